@@ -1,0 +1,311 @@
+// capi.cu -- the C-ABI of libdpmsolver_b200.so (see include/dpm_solver_b200.h)
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "launch.cuh"
+
+namespace dpm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_variant{0}, g_threads{0}, g_ctas{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = 148;
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+int max_smem_optin() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 227 * 1024;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        v <= 0)
+      v = 227 * 1024;
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+static inline int esize(int dt) { return dt == DPM_F32 ? 4 : 2; }
+static inline bool valid_dtype(int dt) { return dt == DPM_F32 || dt == DPM_BF16 || dt == DPM_F16; }
+static inline bool aligned(const void* p, int dt) {
+  const uintptr_t a = dt == DPM_F32 ? 32 : 16;
+  return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0;
+}
+static inline const void* off(const void* p, int dt, uint64_t elems) {
+  return p ? static_cast<const char*>(p) + elems * esize(dt) : nullptr;
+}
+static inline void* off(void* p, int dt, uint64_t elems) {
+  return p ? static_cast<char*>(p) + elems * esize(dt) : nullptr;
+}
+
+struct Needs {
+  bool x, m0, m1, m2, ec, eu, xe;
+};
+
+// validate a descriptor and translate it into the kernel parameter block
+static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for_quantile) {
+  if (d == nullptr) { set_error("desc is NULL"); return DPM_ERR_ARG; }
+  if (!valid_dtype(d->state_dtype) || !valid_dtype(d->model_dtype)) {
+    set_error("bad dtype (state %d, model %d)", d->state_dtype, d->model_dtype);
+    return DPM_ERR_ARG;
+  }
+  const int form = for_quantile ? DPM_FORM_NONE : d->form;
+  if (form < DPM_FORM_NONE || form > DPM_FORM_SS3T) { set_error("bad form %d", form); return DPM_ERR_ARG; }
+  if (d->n_model < 0 || d->n_model > 2) { set_error("n_model must be 0, 1 or 2"); return DPM_ERR_ARG; }
+  if (d->param < DPM_PARAM_NOISE || d->param > DPM_PARAM_SCORE) { set_error("bad param %d", d->param); return DPM_ERR_ARG; }
+  if ((d->n >> 3) > 0xffffffffull) { set_error("n too large (max 2^35-1 elements per call)"); return DPM_ERR_ARG; }
+
+  nd->x = form != DPM_FORM_NONE;
+  nd->m0 = d->n_model == 0;
+  nd->m1 = form == DPM_FORM_LIN2 || form == DPM_FORM_LIN3 || form == DPM_FORM_DIFF2 ||
+           form == DPM_FORM_MS3 || form == DPM_FORM_SS3T;
+  nd->m2 = form == DPM_FORM_LIN3 || form == DPM_FORM_MS3 || form == DPM_FORM_SS3T;
+  nd->ec = d->n_model >= 1;
+  nd->eu = d->n_model == 2;
+  nd->xe = d->n_model >= 1 && (d->param == DPM_PARAM_X_START || d->param == DPM_PARAM_V || d->predict_x0);
+
+  if (for_quantile) {
+    if (d->n_model < 1 || !d->predict_x0) { set_error("dynamic threshold needs n_model >= 1 and predict_x0"); return DPM_ERR_ARG; }
+  } else {
+    if (form == DPM_FORM_NONE && (d->n_model == 0 || d->m_out == nullptr)) {
+      set_error("form NONE needs n_model >= 1 and m_out");
+      return DPM_ERR_ARG;
+    }
+    if (form != DPM_FORM_NONE && d->out == nullptr) { set_error("out is NULL"); return DPM_ERR_ARG; }
+  }
+  const void* xe = d->xe ? d->xe : d->x;
+  if ((nd->x && !d->x) || (nd->m0 && !d->m0) || (nd->m1 && !d->m1) || (nd->m2 && !d->m2) ||
+      (nd->ec && !d->e_cond) || (nd->eu && !d->e_uncond) || (nd->xe && !xe)) {
+    set_error("a tensor required by form %d / n_model %d is NULL", form, d->n_model);
+    return DPM_ERR_ARG;
+  }
+  if (d->thr != nullptr || for_quantile) {
+    if (d->per_sample == 0 || d->n % d->per_sample != 0) { set_error("n must be a multiple of per_sample"); return DPM_ERR_ARG; }
+    if (!for_quantile && (d->n_model == 0 || !d->predict_x0)) { set_error("thr requires n_model >= 1 and predict_x0"); return DPM_ERR_ARG; }
+  }
+
+  memset(kp, 0, sizeof(*kp));
+  kp->x = d->x; kp->xe = xe; kp->m0 = d->m0; kp->m1 = d->m1; kp->m2 = d->m2;
+  kp->ec = d->e_cond; kp->eu = d->e_uncond;
+  kp->m_out = for_quantile ? nullptr : d->m_out;
+  kp->out = for_quantile ? nullptr : d->out;
+  kp->thr = for_quantile ? nullptr : d->thr;
+  kp->n = d->n;
+  kp->npk = (uint32_t)(d->n / kPacket);
+  kp->per_sample = d->per_sample ? d->per_sample : 1;
+  kp->pk_per_sample = (d->per_sample % kPacket == 0) ? (uint32_t)(d->per_sample / kPacket) : 0;
+  kp->elem_offset = 0;
+  kp->param = d->param; kp->predict_x0 = d->predict_x0 ? 1 : 0; kp->c0_on_old = d->c0_on_old ? 1 : 0;
+  kp->use_xe = nd->xe ? 1 : 0;
+  kp->xe_is_x = (nd->xe && nd->x && xe == d->x) ? 1 : 0;
+  kp->form = form; kp->n_model = d->n_model;
+  kp->state_dtype = d->state_dtype; kp->model_dtype = d->model_dtype;
+  kp->guidance = d->guidance; kp->alpha_e = d->alpha_e; kp->sigma_e = d->sigma_e;
+  kp->a = d->a; kp->c0 = d->c0; kp->c1 = d->c1; kp->c2 = d->c2;
+  kp->w0 = d->w0; kp->w1 = d->w1; kp->w2 = d->w2; kp->w3 = d->w3; kp->w4 = d->w4;
+  return DPM_OK;
+}
+
+static bool all_aligned(const KParams& p, const Needs& nd) {
+  const int sd = p.state_dtype, md = p.model_dtype;
+  bool ok = true;
+  if (nd.x) ok &= aligned(p.x, sd);
+  if (nd.xe) ok &= aligned(p.xe, sd);
+  if (nd.m0) ok &= aligned(p.m0, sd);
+  if (nd.m1) ok &= aligned(p.m1, sd);
+  if (nd.m2) ok &= aligned(p.m2, sd);
+  if (nd.ec) ok &= aligned(p.ec, md);
+  if (nd.eu) ok &= aligned(p.eu, md);
+  if (p.m_out) ok &= aligned(p.m_out, sd);
+  if (p.out) ok &= aligned(p.out, sd);
+  return ok;
+}
+
+static KParams shifted(const KParams& p, uint64_t elems) {
+  KParams t = p;
+  const int sd = p.state_dtype, md = p.model_dtype;
+  t.x = off(p.x, sd, elems); t.xe = off(p.xe, sd, elems); t.m0 = off(p.m0, sd, elems);
+  t.m1 = off(p.m1, sd, elems); t.m2 = off(p.m2, sd, elems);
+  t.ec = off(p.ec, md, elems); t.eu = off(p.eu, md, elems);
+  t.m_out = off(p.m_out, sd, elems); t.out = off(p.out, sd, elems);
+  t.n = p.n - elems;
+  t.elem_offset = elems;
+  return t;
+}
+
+static int finish(cudaStream_t) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("CUDA launch failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  return DPM_OK;
+}
+
+static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
+  KParams p;
+  Needs nd;
+  int rc = build_params(d, &p, &nd, false);
+  if (rc != DPM_OK) return rc;
+  if (p.n == 0) return DPM_OK;
+  Tuning t{g_variant.load(), g_threads.load(), g_ctas.load()};
+
+  bool body_done = false;
+  if (p.npk > 0 && all_aligned(p, nd)) {
+    int r = 1;
+    if (t.variant == 1) r = launch_step_tma(p, t, stream);
+    if (r == 1) r = launch_step_direct(p, t, stream);
+    if (r < 0 || r > 1) return r;
+    body_done = (r == 0);
+  }
+  if (!body_done) {
+    rc = launch_step_scalar(p, stream);  // whole range on the generic kernel
+  } else if (p.n % kPacket) {
+    rc = launch_step_scalar(shifted(p, (uint64_t)p.npk * kPacket), stream);  // tail
+  }
+  if (rc != DPM_OK) return rc;
+  return finish(stream);
+}
+
+}  // namespace dpm
+
+using namespace dpm;
+
+extern "C" {
+
+int dpm_version(void) { return DPM_B200_VERSION; }
+const char* dpm_last_error(void) { return g_err; }
+uint64_t dpm_launch_count(void) { return g_launches.load(); }
+
+int dpm_set_tuning(int variant, int threads, int ctas_per_sm) {
+  if (variant < 0 || variant > 1) { set_error("variant must be 0 or 1"); return DPM_ERR_ARG; }
+  if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) { set_error("threads must be a multiple of 32 in [32,512]"); return DPM_ERR_ARG; }
+  if (ctas_per_sm < 0 || ctas_per_sm > 32) { set_error("ctas_per_sm must be in [0,32]"); return DPM_ERR_ARG; }
+  g_variant = variant; g_threads = threads; g_ctas = ctas_per_sm;
+  return DPM_OK;
+}
+int dpm_get_tuning(int* variant, int* threads, int* ctas_per_sm) {
+  if (variant) *variant = g_variant.load();
+  if (threads) *threads = g_threads.load();
+  if (ctas_per_sm) *ctas_per_sm = g_ctas.load();
+  return DPM_OK;
+}
+
+int dpm_step(const dpm_step_desc* desc, dpm_stream_t stream) {
+  return step_impl(desc, static_cast<cudaStream_t>(stream));
+}
+
+static dpm_step_desc base_desc(void* out, const void* x, uint64_t n, int dtype, int form) {
+  dpm_step_desc d;
+  memset(&d, 0, sizeof(d));
+  d.out = out; d.x = x; d.n = n; d.state_dtype = dtype; d.model_dtype = dtype; d.form = form;
+  return d;
+}
+
+int dpm_lincomb(void* out, const void* x, const void* m0, const void* m1, const void* m2, int k,
+                float a, float c0, float c1, float c2, uint64_t n, int dtype, dpm_stream_t stream) {
+  if (k < 1 || k > 3) { set_error("k must be 1, 2 or 3"); return DPM_ERR_ARG; }
+  dpm_step_desc d = base_desc(out, x, n, dtype, k == 1 ? DPM_FORM_LIN1 : k == 2 ? DPM_FORM_LIN2 : DPM_FORM_LIN3);
+  d.m0 = m0; d.m1 = m1; d.m2 = m2; d.a = a; d.c0 = c0; d.c1 = c1; d.c2 = c2;
+  return dpm_step(&d, stream);
+}
+
+int dpm_solver_first_update(void* x_t, const void* x, const void* model_s, float a, float c0,
+                            uint64_t n, int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(x_t, x, n, dtype, DPM_FORM_LIN1);
+  d.m0 = model_s; d.a = a; d.c0 = c0;
+  return dpm_step(&d, stream);
+}
+
+int dpm_multistep_second_update(void* x_t, const void* x, const void* model_prev_0,
+                                const void* model_prev_1, float a, float c0, float c1,
+                                float inv_r0, uint64_t n, int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(x_t, x, n, dtype, DPM_FORM_DIFF2);
+  d.m0 = model_prev_0; d.m1 = model_prev_1; d.a = a; d.c0 = c0; d.c1 = c1; d.w0 = inv_r0;
+  return dpm_step(&d, stream);
+}
+
+int dpm_multistep_third_update(void* x_t, const void* x, const void* model_prev_0,
+                               const void* model_prev_1, const void* model_prev_2, float a,
+                               float c0, float c1, float c2, float inv_r0, float inv_r1, float w,
+                               float q, uint64_t n, int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(x_t, x, n, dtype, DPM_FORM_MS3);
+  d.m0 = model_prev_0; d.m1 = model_prev_1; d.m2 = model_prev_2;
+  d.a = a; d.c0 = c0; d.c1 = c1; d.c2 = c2; d.w0 = inv_r0; d.w1 = inv_r1; d.w2 = w; d.w3 = q;
+  return dpm_step(&d, stream);
+}
+
+int dpm_singlestep_diff_update(void* x_t, const void* x, const void* model_s,
+                               const void* model_new, float a, float c0, float c1, uint64_t n,
+                               int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(x_t, x, n, dtype, DPM_FORM_DIFF2);
+  d.m0 = model_new; d.m1 = model_s; d.a = a; d.c0 = c0; d.c1 = c1; d.w0 = 1.f; d.c0_on_old = 1;
+  return dpm_step(&d, stream);
+}
+
+int dpm_singlestep_third_taylor_update(void* x_t, const void* x, const void* model_s,
+                                       const void* model_s1, const void* model_s2, float a,
+                                       float c0, float c1, float c2, float inv_r1, float inv_r2,
+                                       float r2, float r1, float r2_minus_r1, uint64_t n,
+                                       int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(x_t, x, n, dtype, DPM_FORM_SS3T);
+  d.m0 = model_s2; d.m1 = model_s1; d.m2 = model_s;
+  d.a = a; d.c0 = c0; d.c1 = c1; d.c2 = c2;
+  d.w0 = inv_r1; d.w1 = inv_r2; d.w2 = r2; d.w3 = r1; d.w4 = r2_minus_r1;
+  return dpm_step(&d, stream);
+}
+
+int dpm_cfg_combine(void* eps, const void* eps_uncond, const void* eps_cond, float scale,
+                    uint64_t n, int dtype, dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(nullptr, nullptr, n, dtype, DPM_FORM_NONE);
+  d.n_model = 2; d.e_cond = eps_cond; d.e_uncond = eps_uncond; d.guidance = scale;
+  d.m_out = eps; d.param = DPM_PARAM_NOISE; d.predict_x0 = 0;
+  return dpm_step(&d, stream);
+}
+
+int dpm_data_prediction(void* x0, const void* x, const void* eps, float alpha_t, float sigma_t,
+                        const float* thr, uint64_t per_sample, uint64_t n, int dtype,
+                        dpm_stream_t stream) {
+  dpm_step_desc d = base_desc(nullptr, nullptr, n, dtype, DPM_FORM_NONE);
+  d.n_model = 1; d.e_cond = eps; d.xe = x; d.m_out = x0; d.predict_x0 = 1;
+  d.alpha_e = alpha_t; d.sigma_e = sigma_t; d.thr = thr; d.per_sample = per_sample;
+  return dpm_step(&d, stream);
+}
+
+int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, float max_val,
+                          dpm_stream_t stream) {
+  if (s_out == nullptr) { set_error("s_out is NULL"); return DPM_ERR_ARG; }
+  if (!(q >= 0.f && q <= 1.f)) { set_error("q must be in [0,1]"); return DPM_ERR_ARG; }
+  KParams p;
+  Needs nd;
+  int rc = build_params(desc, &p, &nd, true);
+  if (rc != DPM_OK) return rc;
+  if (p.n == 0) return DPM_OK;
+  rc = launch_quantile(s_out, p, p.n / p.per_sample, q, max_val, static_cast<cudaStream_t>(stream));
+  if (rc != DPM_OK) return rc;
+  return finish(static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

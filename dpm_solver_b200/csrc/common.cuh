@@ -1,0 +1,261 @@
+// common.cuh -- shared device code for the DPM-Solver step kernels (sm_100a).
+//
+// The per-element arithmetic below restates, in fp32 registers, the expression trees of
+// /root/reference/dpm_solver_pytorch.py (line numbers cited inline). The translation unit is
+// compiled with -fmad=false: every product and every sum is rounded separately, exactly as the
+// reference's chain of eager elementwise ops does, so fp32 results are bit-identical.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dpm_solver_b200.h"
+
+namespace dpm {
+
+constexpr int kPacket = 8;  // elements per thread-packet: 32 B of fp32 (LDG.256) / 16 B of 16-bit
+
+// ---- kernel parameter block (passed by value, __grid_constant__) -------------------------
+struct KParams {
+  const void* x;
+  const void* xe;
+  const void* m0;
+  const void* m1;
+  const void* m2;
+  const void* ec;
+  const void* eu;
+  void* m_out;
+  void* out;
+  const float* thr;
+  uint64_t n;           // elements (scalar kernel) / unused by packet kernels
+  uint32_t npk;         // number of full packets
+  uint32_t pk_per_sample;  // per_sample / 8 when per_sample % 8 == 0, else 0
+  uint64_t per_sample;
+  uint64_t elem_offset;  // global index of element 0 (tail launches), for thr lookup
+  int32_t param;
+  int32_t predict_x0;
+  int32_t c0_on_old;
+  int32_t use_xe;    // conversion reads the evaluation state
+  int32_t xe_is_x;   // ... and it is the same tensor as x (load once)
+  int32_t form;      // runtime copies (scalar kernel only)
+  int32_t n_model;
+  int32_t state_dtype;
+  int32_t model_dtype;
+  float guidance, alpha_e, sigma_e;
+  float a, c0, c1, c2;
+  float w0, w1, w2, w3, w4;
+};
+
+// ---- storage types ------------------------------------------------------------------------
+template <typename T> struct Raw;  // one packet as loaded (still packed)
+template <> struct Raw<float> { uint32_t r[8]; };
+template <> struct Raw<__nv_bfloat16> { uint32_t r[4]; };
+template <> struct Raw<__half> { uint32_t r[4]; };
+
+template <typename T> struct Traits;
+template <> struct Traits<float> { static constexpr int kBytes = 4; static constexpr int kCode = DPM_F32; };
+template <> struct Traits<__nv_bfloat16> { static constexpr int kBytes = 2; static constexpr int kCode = DPM_BF16; };
+template <> struct Traits<__half> { static constexpr int kBytes = 2; static constexpr int kCode = DPM_F16; };
+
+// Streaming global access: bypass L1 allocation (each byte is touched once per launch).
+// Plain (coherent) ld.global so that `out` may alias `x` element-wise.
+__device__ __forceinline__ void ldg_pk(Raw<float>& v, const float* p) {
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]),
+                 "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "l"(p));
+}
+template <typename T16>
+__device__ __forceinline__ void ldg_pk(Raw<T16>& v, const T16* p) {
+  asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_pk(float* p, const Raw<float>& v) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]),
+               "r"(v.r[6]), "r"(v.r[7])
+               : "memory");
+}
+template <typename T16>
+__device__ __forceinline__ void stg_pk(T16* p, const Raw<T16>& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.r[0]),
+               "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3])
+               : "memory");
+}
+
+// shared-memory packet access (TMA variant)
+__device__ __forceinline__ void lds_pk(Raw<float>& v, const float* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  v.r[0] = a.x; v.r[1] = a.y; v.r[2] = a.z; v.r[3] = a.w;
+  v.r[4] = b.x; v.r[5] = b.y; v.r[6] = b.z; v.r[7] = b.w;
+}
+template <typename T16>
+__device__ __forceinline__ void lds_pk(Raw<T16>& v, const T16* p) {
+  uint4 a = *reinterpret_cast<const uint4*>(p);
+  v.r[0] = a.x; v.r[1] = a.y; v.r[2] = a.z; v.r[3] = a.w;
+}
+__device__ __forceinline__ void sts_pk(float* p, const Raw<float>& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(v.r[0], v.r[1], v.r[2], v.r[3]);
+  q[1] = make_uint4(v.r[4], v.r[5], v.r[6], v.r[7]);
+}
+template <typename T16>
+__device__ __forceinline__ void sts_pk(T16* p, const Raw<T16>& v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v.r[0], v.r[1], v.r[2], v.r[3]);
+}
+
+// unpack / pack -----------------------------------------------------------------------------
+__device__ __forceinline__ void unpack(const Raw<float>& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v.r[i]);
+}
+__device__ __forceinline__ void unpack(const Raw<__nv_bfloat16>& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(v.r[i] << 16);
+    f[2 * i + 1] = __uint_as_float(v.r[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void unpack(const Raw<__half>& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = *reinterpret_cast<const __half2*>(&v.r[i]);
+    float2 t = __half22float2(h);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void pack(Raw<float>& v, const float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v.r[i] = __float_as_uint(f[i]);
+}
+__device__ __forceinline__ void pack(Raw<__nv_bfloat16>& v, const float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    v.r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ void pack(Raw<__half>& v, const float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    v.r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// value as it will read back from storage (so fused and unfused paths agree bit for bit)
+template <typename T> __device__ __forceinline__ float round_storage(float v);
+template <> __device__ __forceinline__ float round_storage<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_storage<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+template <> __device__ __forceinline__ float round_storage<__half>(float v) {
+  return __half2float(__float2half_rn(v));
+}
+
+// dtype-generic scalar access (generic kernel, quantile fallback)
+__device__ __forceinline__ float load_any(const void* p, int dt, size_t i) {
+  switch (dt) {
+    case DPM_BF16: return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+    case DPM_F16: return __half2float(static_cast<const __half*>(p)[i]);
+    default: return static_cast<const float*>(p)[i];
+  }
+}
+__device__ __forceinline__ float store_any(void* p, int dt, size_t i, float v) {
+  switch (dt) {
+    case DPM_BF16: {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      static_cast<__nv_bfloat16*>(p)[i] = h;
+      return __bfloat162float(h);
+    }
+    case DPM_F16: {
+      __half h = __float2half_rn(v);
+      static_cast<__half*>(p)[i] = h;
+      return __half2float(h);
+    }
+    default: static_cast<float*>(p)[i] = v; return v;
+  }
+}
+__device__ __forceinline__ float round_any(int dt, float v) {
+  switch (dt) {
+    case DPM_BF16: return round_storage<__nv_bfloat16>(v);
+    case DPM_F16: return round_storage<__half>(v);
+    default: return v;
+  }
+}
+
+// ---- per-element arithmetic -----------------------------------------------------------------
+// model_wrapper.noise_pred_fn :288-298
+__device__ __forceinline__ float convert_param(int param, float out, float xe, float alpha,
+                                               float sigma) {
+  switch (param) {
+    case DPM_PARAM_X_START: return (xe - alpha * out) / sigma;   // :292
+    case DPM_PARAM_V: return alpha * out + sigma * xe;           // :295
+    case DPM_PARAM_SCORE: return (-sigma) * out;                 // :298
+    default: return out;                                         // :289
+  }
+}
+
+// raw network output(s) -> buffered model value (eps, or x0 for dpmsolver++)
+template <int NE>
+__device__ __forceinline__ float model_value(const KParams& p, float xe, float ec, float eu,
+                                             float thr, bool clamp) {
+  float eps = convert_param(p.param, ec, xe, p.alpha_e, p.sigma_e);
+  if (NE == 2) {
+    float epu = convert_param(p.param, eu, xe, p.alpha_e, p.sigma_e);
+    eps = epu + p.guidance * (eps - epu);  // model_wrapper.model_fn :330
+  }
+  if (p.predict_x0) {
+    float x0 = (xe - p.sigma_e * eps) / p.alpha_e;  // data_prediction_fn :439
+    if (clamp) x0 = fminf(fmaxf(x0, -thr), thr) / thr;  // dynamic_thresholding_fn :424
+    return x0;
+  }
+  return eps;
+}
+
+// the update. T0 = newest model value, m1/m2 = older buffers.
+template <int FORM>
+__device__ __forceinline__ float update_value(const KParams& p, float x, float T0, float m1,
+                                              float m2) {
+  if (FORM == DPM_FORM_LIN1) {
+    return p.a * x + p.c0 * T0;  // :573-576 / :585-588
+  } else if (FORM == DPM_FORM_LIN2) {
+    return (p.a * x + p.c0 * T0) + p.c1 * m1;
+  } else if (FORM == DPM_FORM_LIN3) {
+    return ((p.a * x + p.c0 * T0) + p.c1 * m1) + p.c2 * m2;
+  } else if (FORM == DPM_FORM_DIFF2) {
+    float D = p.w0 * (T0 - m1);              // :823 (w0 = 1/r0) or :639 (w0 = 1)
+    float lead = p.c0_on_old ? m1 : T0;      // singlestep: coefficient sits on model_s
+    return (p.a * x + p.c0 * lead) + p.c1 * D;  // :827-851, :636-669, :728-739
+  } else if (FORM == DPM_FORM_MS3) {
+    float D10 = p.w0 * (T0 - m1);   // :880
+    float D11 = p.w1 * (m1 - m2);   // :881
+    float dd = D10 - D11;
+    float D1 = D10 + p.w2 * dd;     // :882
+    float D2 = p.w3 * dd;           // :883
+    return ((p.a * x + p.c0 * T0) + p.c1 * D1) + p.c2 * D2;  // :888-893 / :898-903
+  } else if (FORM == DPM_FORM_SS3T) {
+    // m2 = model_s, m1 = model_s1, T0 = model_s2
+    float D10 = p.w0 * (m1 - m2);                 // :741
+    float D11 = p.w1 * (T0 - m2);                 // :742
+    float D1 = (p.w2 * D10 - p.w3 * D11) / p.w4;  // :743
+    float D2 = (2.f * (D11 - D10)) / p.w4;        // :744
+    return ((p.a * x + p.c0 * m2) + p.c1 * D1) + p.c2 * D2;  // :745-750 / :784-789
+  }
+  return 0.f;
+}
+
+// compile-time stream requirements of a form
+template <int FORM> struct FormNeeds {
+  static constexpr bool kX = FORM != DPM_FORM_NONE;
+  static constexpr bool kM1 = FORM == DPM_FORM_LIN2 || FORM == DPM_FORM_LIN3 ||
+                              FORM == DPM_FORM_DIFF2 || FORM == DPM_FORM_MS3 ||
+                              FORM == DPM_FORM_SS3T;
+  static constexpr bool kM2 = FORM == DPM_FORM_LIN3 || FORM == DPM_FORM_MS3 || FORM == DPM_FORM_SS3T;
+};
+
+}  // namespace dpm

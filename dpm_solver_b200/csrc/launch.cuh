@@ -1,0 +1,28 @@
+// launch.cuh -- host-side helpers shared by the translation units of libdpmsolver_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace dpm {
+
+struct Tuning {
+  int variant;      // 0 direct, 1 TMA ring
+  int threads;      // threads per CTA (0 = default)
+  int ctas_per_sm;  // persistent-grid CTAs per SM (0 = default)
+};
+
+int sm_count();                     // SMs of the current device (cached per device)
+int max_smem_optin();               // max opt-in dynamic shared memory per CTA
+void count_launch();                // bump the library launch counter
+void set_error(const char* fmt, ...);
+
+// each returns 0 on launch, 1 if this variant does not serve the request, <0 / cudaError on error
+int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream);
+int launch_step_scalar(const KParams& p, cudaStream_t stream);
+int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream);
+int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q, float max_val,
+                    cudaStream_t stream);
+
+}  // namespace dpm

@@ -1,0 +1,221 @@
+// step_direct.cu -- variant 0: persistent grid, 128/256-bit global loads straight to registers.
+//
+// One thread owns kUnroll packets of 8 consecutive elements per tile; all loads of a tile are
+// issued before the first use so that (streams x kUnroll) 16/32-byte requests are in flight per
+// thread. HBM-bound: (k+2)*s algorithmic bytes per element for a pure order-k update.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace dpm {
+
+#ifndef DPM_UNROLL
+#define DPM_UNROLL 2
+#endif
+constexpr int kUnroll = DPM_UNROLL;
+constexpr int kMaxThreads = 512;
+
+template <typename TE, typename TS, int NE, int FORM>
+__global__ void __launch_bounds__(kMaxThreads)
+    k_step_direct(const __grid_constant__ KParams p) {
+  using Needs = FormNeeds<FORM>;
+  const TS* __restrict__ gx = static_cast<const TS*>(p.x);
+  const TS* __restrict__ gxe = static_cast<const TS*>(p.xe);
+  const TS* __restrict__ gm0 = static_cast<const TS*>(p.m0);
+  const TS* __restrict__ gm1 = static_cast<const TS*>(p.m1);
+  const TS* __restrict__ gm2 = static_cast<const TS*>(p.m2);
+  const TE* __restrict__ gec = static_cast<const TE*>(p.ec);
+  const TE* __restrict__ geu = static_cast<const TE*>(p.eu);
+  TS* __restrict__ gmo = static_cast<TS*>(p.m_out);
+  TS* __restrict__ go = static_cast<TS*>(p.out);
+
+  const uint32_t npk = p.npk;
+  const uint32_t tile_pk = blockDim.x * kUnroll;
+  const bool sep_xe = (NE > 0) && p.use_xe && !(Needs::kX && p.xe_is_x);
+  const bool clamp = (NE > 0) && (p.thr != nullptr);
+
+  for (uint64_t tile0 = (uint64_t)blockIdx.x * tile_pk; tile0 < npk;
+       tile0 += (uint64_t)gridDim.x * tile_pk) {
+    Raw<TS> rx[kUnroll], rxe[kUnroll], rm0[kUnroll], rm1[kUnroll], rm2[kUnroll];
+    Raw<TE> rec[kUnroll], reu[kUnroll];
+    // ---- issue every load of the tile ----
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t pk = tile0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      if (pk < npk) {
+        const size_t e = (size_t)pk * kPacket;
+        if (Needs::kX) ldg_pk(rx[u], gx + e);
+        if (NE > 0) {
+          ldg_pk(rec[u], gec + e);
+          if (NE == 2) ldg_pk(reu[u], geu + e);
+          if (sep_xe) ldg_pk(rxe[u], gxe + e);
+        } else {
+          ldg_pk(rm0[u], gm0 + e);
+        }
+        if (Needs::kM1) ldg_pk(rm1[u], gm1 + e);
+        if (Needs::kM2) ldg_pk(rm2[u], gm2 + e);
+      }
+    }
+    // ---- compute + store ----
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t pk = tile0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      if (pk < npk) {
+        const size_t e = (size_t)pk * kPacket;
+        float fx[8], fxe[8], fT[8], fm1[8], fm2[8], fo[8];
+        if (Needs::kX) unpack(rx[u], fx);
+        if (Needs::kM1) unpack(rm1[u], fm1);
+        if (Needs::kM2) unpack(rm2[u], fm2);
+        if (NE > 0) {
+          float fec[8], feu[8];
+          unpack(rec[u], fec);
+          if (NE == 2) unpack(reu[u], feu);
+          if (sep_xe) {
+            unpack(rxe[u], fxe);
+          } else if (Needs::kX) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fxe[i] = fx[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fxe[i] = 0.f;
+          }
+          float thr_pk = 1.f;
+          if (clamp && p.pk_per_sample)
+            thr_pk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float thr = thr_pk;
+            if (clamp && !p.pk_per_sample)
+              thr = __ldg(p.thr + (e + i) / p.per_sample);
+            float mv = model_value<NE>(p, fxe[i], fec[i], NE == 2 ? feu[i] : 0.f, thr, clamp);
+            fT[i] = round_storage<TS>(mv);
+          }
+          if (gmo != nullptr) {
+            Raw<TS> rmo;
+            pack(rmo, fT);
+            stg_pk(gmo + e, rmo);
+          }
+        } else {
+          unpack(rm0[u], fT);
+        }
+        if (FORM != DPM_FORM_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f,
+                                       Needs::kM2 ? fm2[i] : 0.f);
+          Raw<TS> ro;
+          pack(ro, fo);
+          stg_pk(go + e, ro);
+        }
+      }
+    }
+  }
+}
+
+// ---- fully generic element-wise kernel: any dtype mix, any alignment, tails ------------------
+__global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KParams p) {
+  const int sd = p.state_dtype, md = p.model_dtype;
+  const bool need_x = p.form != DPM_FORM_NONE;
+  const bool need_m1 = p.form == DPM_FORM_LIN2 || p.form == DPM_FORM_LIN3 ||
+                       p.form == DPM_FORM_DIFF2 || p.form == DPM_FORM_MS3 ||
+                       p.form == DPM_FORM_SS3T;
+  const bool need_m2 = p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
+  const bool clamp = p.n_model > 0 && p.thr != nullptr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float x = need_x ? load_any(p.x, sd, i) : 0.f;
+    float m1 = need_m1 ? load_any(p.m1, sd, i) : 0.f;
+    float m2 = need_m2 ? load_any(p.m2, sd, i) : 0.f;
+    float T0;
+    if (p.n_model > 0) {
+      float xe = p.use_xe ? ((need_x && p.xe_is_x) ? x : load_any(p.xe, sd, i)) : 0.f;
+      float ec = load_any(p.ec, md, i);
+      float eu = p.n_model == 2 ? load_any(p.eu, md, i) : 0.f;
+      float thr = clamp ? p.thr[(i + p.elem_offset) / p.per_sample] : 1.f;
+      float mv = p.n_model == 2 ? model_value<2>(p, xe, ec, eu, thr, clamp)
+                                : model_value<1>(p, xe, ec, eu, thr, clamp);
+      T0 = round_any(sd, mv);
+      if (p.m_out) store_any(p.m_out, sd, i, mv);
+    } else {
+      T0 = load_any(p.m0, sd, i);
+    }
+    float o;
+    switch (p.form) {
+      case DPM_FORM_LIN1: o = update_value<DPM_FORM_LIN1>(p, x, T0, m1, m2); break;
+      case DPM_FORM_LIN2: o = update_value<DPM_FORM_LIN2>(p, x, T0, m1, m2); break;
+      case DPM_FORM_LIN3: o = update_value<DPM_FORM_LIN3>(p, x, T0, m1, m2); break;
+      case DPM_FORM_DIFF2: o = update_value<DPM_FORM_DIFF2>(p, x, T0, m1, m2); break;
+      case DPM_FORM_MS3: o = update_value<DPM_FORM_MS3>(p, x, T0, m1, m2); break;
+      case DPM_FORM_SS3T: o = update_value<DPM_FORM_SS3T>(p, x, T0, m1, m2); break;
+      default: continue;
+    }
+    store_any(p.out, sd, i, o);
+  }
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------
+typedef void (*StepKernel)(const KParams);
+
+template <typename TE, typename TS, int NE>
+static StepKernel pick_form(int form) {
+  switch (form) {
+    case DPM_FORM_NONE: return NE > 0 ? k_step_direct<TE, TS, NE, DPM_FORM_NONE> : nullptr;
+    case DPM_FORM_LIN1: return k_step_direct<TE, TS, NE, DPM_FORM_LIN1>;
+    case DPM_FORM_LIN2: return k_step_direct<TE, TS, NE, DPM_FORM_LIN2>;
+    case DPM_FORM_LIN3: return k_step_direct<TE, TS, NE, DPM_FORM_LIN3>;
+    case DPM_FORM_DIFF2: return k_step_direct<TE, TS, NE, DPM_FORM_DIFF2>;
+    case DPM_FORM_MS3: return k_step_direct<TE, TS, NE, DPM_FORM_MS3>;
+    case DPM_FORM_SS3T: return k_step_direct<TE, TS, NE, DPM_FORM_SS3T>;
+  }
+  return nullptr;
+}
+template <typename TE, typename TS>
+static StepKernel pick_ne(int ne, int form) {
+  switch (ne) {
+    case 1: return pick_form<TE, TS, 1>(form);
+    case 2: return pick_form<TE, TS, 2>(form);
+  }
+  return nullptr;
+}
+static StepKernel pick_direct(int md, int sd, int ne, int form) {
+  if (ne == 0) {
+    switch (sd) {
+      case DPM_F32: return pick_form<float, float, 0>(form);
+      case DPM_BF16: return pick_form<__nv_bfloat16, __nv_bfloat16, 0>(form);
+      case DPM_F16: return pick_form<__half, __half, 0>(form);
+    }
+    return nullptr;
+  }
+  if (md == DPM_F32 && sd == DPM_F32) return pick_ne<float, float>(ne, form);
+  if (md == DPM_BF16 && sd == DPM_BF16) return pick_ne<__nv_bfloat16, __nv_bfloat16>(ne, form);
+  if (md == DPM_F16 && sd == DPM_F16) return pick_ne<__half, __half>(ne, form);
+  if (md == DPM_BF16 && sd == DPM_F32) return pick_ne<__nv_bfloat16, float>(ne, form);
+  if (md == DPM_F16 && sd == DPM_F32) return pick_ne<__half, float>(ne, form);
+  return nullptr;  // other mixes run on the generic kernel
+}
+
+int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream) {
+  StepKernel k = pick_direct(p.model_dtype, p.state_dtype, p.n_model, p.form);
+  if (k == nullptr) return 1;  // not served here
+  const int threads = t.threads > 0 ? t.threads : 256;
+  const uint32_t tile_pk = (uint32_t)threads * kUnroll;
+  uint64_t tiles = ((uint64_t)p.npk + tile_pk - 1) / tile_pk;
+  uint64_t cap = (uint64_t)sm_count() * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 8);
+  uint32_t grid = (uint32_t)(tiles < cap ? tiles : cap);
+  if (grid == 0) return 0;
+  k<<<grid, threads, 0, stream>>>(p);
+  count_launch();
+  return 0;
+}
+
+int launch_step_scalar(const KParams& p, cudaStream_t stream) {
+  if (p.n == 0) return 0;
+  const int threads = 256;
+  uint64_t blocks = (p.n + threads - 1) / threads;
+  uint64_t cap = (uint64_t)sm_count() * 8;
+  uint32_t grid = (uint32_t)(blocks < cap ? blocks : cap);
+  k_step_scalar<<<grid, threads, 0, stream>>>(p);
+  count_launch();
+  return 0;
+}
+
+}  // namespace dpm

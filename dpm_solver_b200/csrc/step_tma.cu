@@ -1,0 +1,273 @@
+// step_tma.cu -- variant 1: TMA bulk staging through a shared-memory ring.
+//
+// Persistent CTAs. One elected thread moves whole tiles with 1-D bulk async copies
+// (cp.async.bulk, SASS UBLKCP): global -> shared completes on an mbarrier (complete_tx),
+// shared -> global is a bulk store tracked by bulk groups. The other threads only touch
+// shared memory (LDS.128 / STS.128) and registers. kStages tiles are in flight per CTA, so
+// the bytes in flight per SM are decoupled from register count and occupancy.
+//
+// Ring protocol for tile i of a CTA (stage s = i % S):
+//   wait full[s] (parity (i/S)&1) -> compute, write results into out-buffers of stage s ->
+//   fence.proxy.async -> thread 0: bulk wait_group.read(S-2) (frees the out-buffers of the
+//   next stage) -> __syncthreads -> thread 0: bulk-store stage s, commit, then refill the
+//   input buffers of stage s with tile i+S.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace dpm {
+
+constexpr int kTmaUnroll = 2;
+constexpr int kTmaMaxThreads = 512;
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offsets of the per-stream tile buffers inside one stage
+struct StageLayout {
+  uint32_t x, ec, eu, m0, m1, m2, mo, o;  // 0xffffffff = stream absent
+  uint32_t bytes;                          // stage size
+};
+
+template <typename TE, typename TS, int NE, int FORM>
+__global__ void __launch_bounds__(kTmaMaxThreads)
+    k_step_tma(const __grid_constant__ KParams p, const __grid_constant__ StageLayout L,
+               const int stages) {
+  using Needs = FormNeeds<FORM>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kMaxStages]
+  unsigned char* ring = smem + 128;
+
+  const int tid = threadIdx.x;
+  const uint32_t tile_pk = blockDim.x * kTmaUnroll;
+  const uint32_t tile_el = tile_pk * kPacket;
+  const uint32_t ntiles = (p.npk + tile_pk - 1) / tile_pk;
+  const bool has_x = Needs::kX || (NE > 0 && p.use_xe);  // state slot: x, or xe when no update
+  const bool clamp = (NE > 0) && (p.thr != nullptr);
+  const bool has_mo = (NE > 0) && (p.m_out != nullptr);
+  const char* gstate = static_cast<const char*>(Needs::kX ? p.x : p.xe);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue_loads = [&](uint32_t tile, int s) {
+    const uint64_t e0 = (uint64_t)tile * tile_el;
+    uint64_t rem = (uint64_t)p.npk * kPacket - e0;
+    const uint32_t el = rem < tile_el ? (uint32_t)rem : tile_el;
+    const uint32_t bs = el * Traits<TS>::kBytes, bm = el * Traits<TE>::kBytes;
+    unsigned char* st = ring + (size_t)s * L.bytes;
+    uint32_t tx = 0;
+    if (has_x) tx += bs;
+    if (NE >= 1) tx += bm;
+    if (NE == 2) tx += bm;
+    if (NE == 0) tx += bs;
+    if (Needs::kM1) tx += bs;
+    if (Needs::kM2) tx += bs;
+    mbar_expect_tx(&full[s], tx);
+    if (has_x) bulk_g2s(st + L.x, gstate + e0 * Traits<TS>::kBytes, bs, &full[s]);
+    if (NE >= 1) bulk_g2s(st + L.ec, static_cast<const char*>(p.ec) + e0 * Traits<TE>::kBytes, bm, &full[s]);
+    if (NE == 2) bulk_g2s(st + L.eu, static_cast<const char*>(p.eu) + e0 * Traits<TE>::kBytes, bm, &full[s]);
+    if (NE == 0) bulk_g2s(st + L.m0, static_cast<const char*>(p.m0) + e0 * Traits<TS>::kBytes, bs, &full[s]);
+    if (Needs::kM1) bulk_g2s(st + L.m1, static_cast<const char*>(p.m1) + e0 * Traits<TS>::kBytes, bs, &full[s]);
+    if (Needs::kM2) bulk_g2s(st + L.m2, static_cast<const char*>(p.m2) + e0 * Traits<TS>::kBytes, bs, &full[s]);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const uint64_t tile = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
+      if (tile < ntiles) issue_loads((uint32_t)tile, s);
+    }
+  }
+
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it % stages;
+    const uint32_t parity = (it / stages) & 1u;
+    unsigned char* st = ring + (size_t)s * L.bytes;
+    const uint64_t e0 = tile * tile_el;
+    const uint64_t rem = (uint64_t)p.npk * kPacket - e0;
+    const uint32_t el = rem < tile_el ? (uint32_t)rem : tile_el;
+    const uint32_t pk_here = el / kPacket;
+
+    mbar_wait(&full[s], parity);
+
+#pragma unroll
+    for (int u = 0; u < kTmaUnroll; ++u) {
+      const uint32_t lp = u * blockDim.x + tid;  // packet inside the tile
+      if (lp < pk_here) {
+        const uint32_t le = lp * kPacket;
+        float fx[8], fT[8], fm1[8], fm2[8], fo[8];
+        if (has_x) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.x) + le); unpack(r, fx); }
+        if (Needs::kM1) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m1) + le); unpack(r, fm1); }
+        if (Needs::kM2) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m2) + le); unpack(r, fm2); }
+        if (NE > 0) {
+          float fec[8], feu[8];
+          { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.ec) + le); unpack(r, fec); }
+          if (NE == 2) { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.eu) + le); unpack(r, feu); }
+          const uint64_t pk = e0 / kPacket + lp;
+          float thr_pk = 1.f;
+          if (clamp && p.pk_per_sample) thr_pk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float thr = thr_pk;
+            if (clamp && !p.pk_per_sample) thr = __ldg(p.thr + (e0 + le + i) / p.per_sample);
+            float mv = model_value<NE>(p, has_x ? fx[i] : 0.f, fec[i], NE == 2 ? feu[i] : 0.f, thr, clamp);
+            fT[i] = round_storage<TS>(mv);
+          }
+          if (has_mo) { Raw<TS> r; pack(r, fT); sts_pk(reinterpret_cast<TS*>(st + L.mo) + le, r); }
+        } else {
+          Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m0) + le); unpack(r, fT);
+        }
+        if (FORM != DPM_FORM_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f, Needs::kM2 ? fm2[i] : 0.f);
+          Raw<TS> r; pack(r, fo); sts_pk(reinterpret_cast<TS*>(st + L.o) + le, r);
+        }
+      }
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the async proxy (bulk store)
+    if (tid == 0) bulk_wait_read(stages - 2);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bs = el * Traits<TS>::kBytes;
+      if (has_mo) bulk_s2g(static_cast<char*>(p.m_out) + e0 * Traits<TS>::kBytes, st + L.mo, bs);
+      if (FORM != DPM_FORM_NONE) bulk_s2g(static_cast<char*>(p.out) + e0 * Traits<TS>::kBytes, st + L.o, bs);
+      bulk_commit();
+      const uint64_t next = tile + (uint64_t)stages * gridDim.x;
+      if (next < ntiles) issue_loads((uint32_t)next, s);
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+typedef void (*TmaKernel)(const KParams, const StageLayout, const int);
+
+template <typename TE, typename TS, int NE>
+static TmaKernel tma_form(int form) {
+  switch (form) {
+    case DPM_FORM_NONE: return NE > 0 ? k_step_tma<TE, TS, NE, DPM_FORM_NONE> : nullptr;
+    case DPM_FORM_LIN1: return k_step_tma<TE, TS, NE, DPM_FORM_LIN1>;
+    case DPM_FORM_DIFF2: return k_step_tma<TE, TS, NE, DPM_FORM_DIFF2>;
+    case DPM_FORM_MS3: return k_step_tma<TE, TS, NE, DPM_FORM_MS3>;
+  }
+  return nullptr;  // LIN2/LIN3/SS3T: direct variant
+}
+template <typename TE, typename TS>
+static TmaKernel tma_ne(int ne, int form) {
+  switch (ne) {
+    case 1: return tma_form<TE, TS, 1>(form);
+    case 2: return tma_form<TE, TS, 2>(form);
+  }
+  return nullptr;
+}
+static TmaKernel pick_tma(int md, int sd, int ne, int form) {
+  if (ne == 0) {
+    if (sd == DPM_F32) return tma_form<float, float, 0>(form);
+    if (sd == DPM_BF16) return tma_form<__nv_bfloat16, __nv_bfloat16, 0>(form);
+    return nullptr;
+  }
+  if (md == DPM_F32 && sd == DPM_F32) return tma_ne<float, float>(ne, form);
+  if (md == DPM_BF16 && sd == DPM_BF16) return tma_ne<__nv_bfloat16, __nv_bfloat16>(ne, form);
+  if (md == DPM_BF16 && sd == DPM_F32) return tma_ne<__nv_bfloat16, float>(ne, form);
+  return nullptr;
+}
+
+int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
+  const bool need_x = p.form != DPM_FORM_NONE;
+  if (p.n_model > 0 && p.use_xe && need_x && !p.xe_is_x) return 1;  // separate xe: direct variant
+  TmaKernel k = pick_tma(p.model_dtype, p.state_dtype, p.n_model, p.form);
+  if (k == nullptr) return 1;
+  const int threads = t.threads > 0 ? t.threads : 256;
+  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
+  const uint32_t tile_el = (uint32_t)threads * kTmaUnroll * kPacket;
+  const uint32_t ss = p.state_dtype == DPM_F32 ? 4 : 2, ms = p.model_dtype == DPM_F32 ? 4 : 2;
+
+  StageLayout L;
+  uint32_t o = 0;
+  auto take = [&](bool on, uint32_t es) { uint32_t r = 0xffffffffu; if (on) { r = o; o += tile_el * es; } return r; };
+  const bool m1 = p.form == DPM_FORM_DIFF2 || p.form == DPM_FORM_MS3;
+  const bool m2 = p.form == DPM_FORM_MS3;
+  L.x = take(need_x || (p.n_model > 0 && p.use_xe), ss);
+  L.ec = take(p.n_model >= 1, ms);
+  L.eu = take(p.n_model == 2, ms);
+  L.m0 = take(p.n_model == 0, ss);
+  L.m1 = take(m1, ss);
+  L.m2 = take(m2, ss);
+  L.mo = take(p.n_model > 0 && p.m_out != nullptr, ss);
+  L.o = take(need_x, ss);
+  L.bytes = o;
+
+  // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
+  const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
+  size_t budget = per_cta < (size_t)max_smem_optin() ? per_cta : (size_t)max_smem_optin();
+  int stages = (int)((budget - 128) / L.bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return 1;
+  const size_t smem = 128 + (size_t)stages * L.bytes;
+
+  const uint32_t tile_pk = (uint32_t)threads * kTmaUnroll;
+  const uint64_t ntiles = ((uint64_t)p.npk + tile_pk - 1) / tile_pk;
+  const uint64_t cap = (uint64_t)sm_count() * ctas;
+  const uint32_t grid = (uint32_t)(ntiles < cap ? ntiles : cap);
+  if (grid == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("tma: smem opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+  k<<<grid, threads, smem, stream>>>(p, L, stages);
+  count_launch();
+  return 0;
+}
+
+}  // namespace dpm

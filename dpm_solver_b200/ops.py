@@ -1,0 +1,219 @@
+"""Tensor-level front end of the C-ABI: one call = one fused kernel launch on the current stream.
+
+`StepArgs` mirrors `struct dpm_step_desc` (include/dpm_solver_b200.h) with torch tensors in place
+of raw pointers. The only executor shipped is `CudaBackend`, which hands device pointers to
+libdpmsolver_b200.so; it refuses CPU tensors (there is no CPU or PyTorch fallback).  Tests may
+install another executor with `set_backend()` to exercise the host-side logic without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (DPM_BF16, DPM_F16, DPM_F32, FORM_DIFF2, FORM_LIN1, FORM_LIN2, FORM_LIN3,
+                   FORM_MS3, FORM_NONE, FORM_SS3T, PARAM_NOISE, StepDesc)
+
+_DTYPE_CODE = {torch.float32: DPM_F32, torch.bfloat16: DPM_BF16, torch.float16: DPM_F16}
+SUPPORTED_DTYPES = tuple(_DTYPE_CODE)
+
+
+@dataclass
+class StepArgs:
+    """One fused solver step (see dpm_step_desc for the meaning of every field)."""
+    form: int = FORM_NONE
+    n_model: int = 0
+    x: Optional[torch.Tensor] = None
+    xe: Optional[torch.Tensor] = None
+    m0: Optional[torch.Tensor] = None
+    m1: Optional[torch.Tensor] = None
+    m2: Optional[torch.Tensor] = None
+    e_cond: Optional[torch.Tensor] = None
+    e_uncond: Optional[torch.Tensor] = None
+    thr: Optional[torch.Tensor] = None
+    per_sample: int = 0
+    param: int = PARAM_NOISE
+    predict_x0: bool = False
+    c0_on_old: bool = False
+    guidance: float = 1.0
+    alpha_e: float = 1.0
+    sigma_e: float = 0.0
+    a: float = 0.0
+    c0: float = 0.0
+    c1: float = 0.0
+    c2: float = 0.0
+    w0: float = 0.0
+    w1: float = 0.0
+    w2: float = 0.0
+    w3: float = 0.0
+    w4: float = 0.0
+    want_m_out: bool = False          # materialise the computed model value (n_model >= 1)
+    state_dtype: Optional[torch.dtype] = None  # dtype of x/xe/m*/outputs; default: from tensors
+    out: Optional[torch.Tensor] = None     # optional preallocated outputs
+    m_out: Optional[torch.Tensor] = None
+
+    def state_tensors(self):
+        return [t for t in (self.x, self.xe, self.m0, self.m1, self.m2) if t is not None]
+
+    def model_tensors(self):
+        return [t for t in (self.e_cond, self.e_uncond) if t is not None]
+
+    def reference_tensor(self) -> torch.Tensor:
+        for t in (self.x, self.xe, self.e_cond, self.m0):
+            if t is not None:
+                return t
+        raise ValueError("StepArgs without tensors")
+
+
+class CudaBackend:
+    """Executes StepArgs through libdpmsolver_b200.so."""
+
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        self._lib = _lib.lib()  # fail loudly at construction if the .so is missing
+
+    # -- helpers --------------------------------------------------------------------------
+    @staticmethod
+    def _check(t: torch.Tensor, what: str, dev, numel: int, dtype=None) -> torch.Tensor:
+        if not t.is_cuda:
+            raise RuntimeError(f"dpm_solver_b200: `{what}` is on {t.device}; this library is CUDA-only "
+                               "(no CPU fallback)")
+        if t.device != dev:
+            raise RuntimeError(f"dpm_solver_b200: `{what}` is on {t.device}, expected {dev}")
+        if t.numel() != numel:
+            raise ValueError(f"dpm_solver_b200: `{what}` has {t.numel()} elements, expected {numel}")
+        if dtype is not None and t.dtype != dtype:
+            raise TypeError(f"dpm_solver_b200: `{what}` is {t.dtype}, expected {dtype}")
+        if t.dtype not in _DTYPE_CODE:
+            raise TypeError(f"dpm_solver_b200: unsupported dtype {t.dtype} for `{what}`")
+        return t if t.is_contiguous() else t.contiguous()
+
+    def _fill(self, a: StepArgs):
+        ref = a.reference_tensor()
+        dev, n = ref.device, ref.numel()
+        sdt = a.state_dtype
+        if sdt is None:
+            st = a.state_tensors()
+            sdt = st[0].dtype if st else a.e_cond.dtype
+        keep = []  # keep contiguous copies alive until after the launch
+        d = StepDesc()
+
+        def ptr(t, what, dtype):
+            if t is None:
+                return None
+            t = self._check(t, what, dev, n, dtype)
+            keep.append(t)
+            return t.data_ptr()
+
+        d.x = ptr(a.x, "x", sdt)
+        d.xe = ptr(a.xe, "xe", sdt)
+        d.m0 = ptr(a.m0, "m0", sdt)
+        d.m1 = ptr(a.m1, "m1", sdt)
+        d.m2 = ptr(a.m2, "m2", sdt)
+        mdt = a.e_cond.dtype if a.e_cond is not None else sdt
+        d.e_cond = ptr(a.e_cond, "e_cond", mdt)
+        d.e_uncond = ptr(a.e_uncond, "e_uncond", mdt)
+        if a.thr is not None:
+            if not a.thr.is_cuda or a.thr.dtype != torch.float32 or not a.thr.is_contiguous():
+                raise TypeError("dpm_solver_b200: `thr` must be a contiguous fp32 CUDA tensor")
+            if a.per_sample <= 0 or n % a.per_sample or a.thr.numel() != n // a.per_sample:
+                raise ValueError("dpm_solver_b200: `thr` needs one value per sample")
+            keep.append(a.thr)
+            d.thr = a.thr.data_ptr()
+        d.n = n
+        d.per_sample = a.per_sample
+        d.state_dtype = _DTYPE_CODE[sdt]
+        d.model_dtype = _DTYPE_CODE[mdt]
+        d.form, d.n_model, d.param = a.form, a.n_model, a.param
+        d.predict_x0, d.c0_on_old = int(a.predict_x0), int(a.c0_on_old)
+        d.guidance, d.alpha_e, d.sigma_e = a.guidance, a.alpha_e, a.sigma_e
+        d.a, d.c0, d.c1, d.c2 = a.a, a.c0, a.c1, a.c2
+        d.w0, d.w1, d.w2, d.w3, d.w4 = a.w0, a.w1, a.w2, a.w3, a.w4
+        return d, keep, ref, sdt
+
+    # -- API -----------------------------------------------------------------------------
+    def step(self, a: StepArgs) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Launch one fused step. Returns (m_out, out); either may be None."""
+        d, keep, ref, sdt = self._fill(a)
+        m_out = out = None
+        if a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE):
+            m_out = a.m_out if a.m_out is not None else torch.empty(ref.shape, dtype=sdt, device=ref.device)
+            self._check(m_out, "m_out", ref.device, ref.numel(), sdt)
+            if not m_out.is_contiguous():
+                raise ValueError("dpm_solver_b200: preallocated m_out must be contiguous")
+            d.m_out = m_out.data_ptr()
+        if a.form != FORM_NONE:
+            out = a.out if a.out is not None else torch.empty(ref.shape, dtype=sdt, device=ref.device)
+            self._check(out, "out", ref.device, ref.numel(), sdt)
+            if not out.is_contiguous():
+                raise ValueError("dpm_solver_b200: preallocated out must be contiguous")
+            d.out = out.data_ptr()
+        with torch.cuda.device(ref.device):
+            stream = torch.cuda.current_stream(ref.device).cuda_stream
+            _lib.check(self._lib.dpm_step(C.byref(d), C.c_void_p(stream)))
+        return m_out, out
+
+    def dynamic_threshold(self, a: StepArgs, q: float, max_val: float) -> torch.Tensor:
+        """Per-sample s_b = max(quantile(|x0_b|, q), max_val) -> fp32 [B] (one launch)."""
+        d, keep, ref, _ = self._fill(a)
+        if a.per_sample <= 0 or ref.numel() % a.per_sample:
+            raise ValueError("dpm_solver_b200: per_sample must divide numel")
+        s = torch.empty(ref.numel() // a.per_sample, dtype=torch.float32, device=ref.device)
+        with torch.cuda.device(ref.device):
+            stream = torch.cuda.current_stream(ref.device).cuda_stream
+            _lib.check(self._lib.dpm_dynamic_threshold(C.c_void_p(s.data_ptr()), C.byref(d),
+                                                       C.c_float(q), C.c_float(max_val),
+                                                       C.c_void_p(stream)))
+        return s
+
+    def launch_count(self) -> int:
+        return int(self._lib.dpm_launch_count())
+
+    def set_tuning(self, variant: int = 0, threads: int = 0, ctas_per_sm: int = 0) -> None:
+        _lib.check(self._lib.dpm_set_tuning(variant, threads, ctas_per_sm))
+
+
+_backend = None
+
+
+def backend():
+    """The active executor (CudaBackend unless a test installed another one)."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b) -> None:
+    """Install an executor with the CudaBackend interface. Used by tests/ only."""
+    global _backend
+    _backend = b
+
+
+# ---- convenience wrappers, named after the reference functions they replace -----------------
+
+def lincomb(x, ms, a, cs, out=None):
+    """out = a*x + sum_j cs[j]*ms[j], 1 <= len(ms) <= 3, unfused fp32 chain, left to right."""
+    k = len(ms)
+    if not 1 <= k <= 3 or len(cs) != k:
+        raise ValueError("lincomb takes 1..3 (tensor, coefficient) pairs")
+    a_ = StepArgs(form=(FORM_LIN1, FORM_LIN2, FORM_LIN3)[k - 1], x=x, m0=ms[0],
+                  m1=ms[1] if k > 1 else None, m2=ms[2] if k > 2 else None, a=a, c0=cs[0],
+                  c1=cs[1] if k > 1 else 0.0, c2=cs[2] if k > 2 else 0.0, out=out)
+    return backend().step(a_)[1]
+
+
+def cfg_combine(eps_uncond, eps_cond, scale):
+    """model_wrapper.model_fn :329-330."""
+    a_ = StepArgs(form=FORM_NONE, n_model=2, e_cond=eps_cond, e_uncond=eps_uncond, guidance=scale,
+                  state_dtype=eps_cond.dtype)
+    return backend().step(a_)[0]
+
+
+__all__ = ["StepArgs", "CudaBackend", "backend", "set_backend", "lincomb", "cfg_combine",
+           "SUPPORTED_DTYPES", "FORM_NONE", "FORM_LIN1", "FORM_LIN2", "FORM_LIN3", "FORM_DIFF2",
+           "FORM_MS3", "FORM_SS3T"]
