@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- solver-update throughput of the DPM-Solver hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+
+One "step" = one full DPM_Solver.sample() over one batch of synthetic input (BASELINE.json
+configs[1]: DPM-Solver++ 2M, 20 solver updates, synthetic eps, bf16 latents [4096,4,64,64] per GPU).
+metric = solver-update GElem/s = elements(x) * updates / seconds, whole job over all N GPUs.
+
+  value     : inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through the public API with HOST buffers: x_T comes from pinned host
+              memory and the result goes back to host inside the timed region
+  roofline  : dominant kernel (fused post-model 2M step): algorithmic bytes / CUDA-event time of
+              every launch inside the timed region, against the measured HBM peak
+  kernels   : the same for each kernel form seen, plus the north-star kernel (fused 3rd-order
+              multistep update at [4096,4,64,64], bf16 and fp32) timed alone
+  cpu_baseline : the reference algorithm on the host cores (oracle, torch-CPU namespace: the same
+              chain of ATen elementwise ops and sort-based interpolation the reference executes)
+
+--impl reference runs only that CPU arm (the unmodified reference is a Python file that does not
+exist on the GPU box; oracle/dpm_oracle.py is its op-for-op restatement, pinned by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (shape per GPU, dtype, algorithm, method, order, steps, cfg scale, thresholding, schedule)
+    "c2": dict(shape=(4096, 4, 64, 64), dtype="bf16", algo="dpmsolver++", method="multistep", order=2, steps=20,
+               cfg=None, thresholding=False, schedule="sd",
+               desc="DPM-Solver++2M, 20 steps, synthetic eps, bf16 latents [4096,4,64,64] per GPU"),
+    "c3": dict(shape=(2048, 4, 64, 64), dtype="bf16", algo="dpmsolver", method="singlestep", order=3, steps=15,
+               cfg=7.5, thresholding=False, schedule="sd",
+               desc="DPM-Solver-3 singlestep, 15 steps, CFG 7.5, bf16 [2048,4,64,64] per GPU"),
+    "c4": dict(shape=(1024, 3, 256, 256), dtype="f32", algo="dpmsolver++", method="multistep", order=3, steps=20,
+               cfg=None, thresholding=True, schedule="ddpm_linear",
+               desc="DPM-Solver++3M + dynamic thresholding, fp32 pixel-space [1024,3,256,256] per GPU"),
+}
+DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
+FORM_NAMES = {0: "convert", 1: "first(lin1)", 2: "lin2", 3: "lin3", 4: "diff2(2M/2S)", 5: "ms3(3M)", 6: "ss3-taylor"}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def n_updates(w):
+    return w["steps"]  # NFE == steps; every model evaluation is followed by exactly one state update
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(w, sample_batch, repeats=1, warmup=0):
+    """Time the oracle (torch-CPU namespace) on a bounded sample of the workload; returns
+    (GElem/s, seconds per sample() call, cores)."""
+    from cases import make_betas
+    from oracle import dpm_oracle as O
+    TH = O.torch_namespace()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, betas = make_betas(w["schedule"])
+    ns = O.VPSchedule.from_betas(betas, xp=TH) if kind == "discrete" else O.VPSchedule("linear", xp=TH)
+    shape = (sample_batch,) + tuple(w["shape"][1:])
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(shape, generator=g)
+    nb = 2 if w["cfg"] else 1
+    banks = [torch.randn((nb * sample_batch,) + shape[1:], generator=g) for _ in range(2)]
+    cnt = [0]
+
+    def net(xx, tt):
+        cnt[0] += 1
+        return banks[cnt[0] % 2]
+
+    smp = O.Sampler(ns, net, algorithm_type=w["algo"], guidance_scale=w["cfg"],
+                    thresholding=(0.995, 1.0) if w["thresholding"] else None)
+
+    def once():
+        if w["method"] == "multistep":
+            return smp.multistep(x, w["steps"], w["order"])
+        return smp.singlestep(x, w["steps"], w["order"])
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            once()
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            once()
+        dt = (time.perf_counter() - t0) / repeats
+    E = int(np.prod(shape))
+    return E * n_updates(w) / dt / 1e9, dt, cores
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 64 if w["shape"][-1] <= 64 else 4
+    val, dt, cores = cpu_arm(w, sample_batch, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    out = {
+        "impl": "reference", "metric": "solver-update GElem/s", "value": val, "unit": "GElem/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": f"batch {sample_batch} of the per-GPU batch, fp32 on CPU"},
+        "cpu_baseline": {"value": val, "unit": "GElem/s", "cores": cores, "kind": "port",
+                         "sample": f"[{sample_batch},{','.join(map(str, w['shape'][1:]))}] fp32, {w['steps']} solver steps per sample() call"},
+        "e2e": {"value": val, "unit": "GElem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def make_timed_backend():
+    from dpm_solver_b200 import ops
+
+    class TimedBackend(ops.CudaBackend):
+        """CudaBackend that brackets every library launch with CUDA events on the launching stream."""
+
+        def __init__(self):
+            super().__init__()
+            self.recording = False
+            self.records = []  # (key, algorithmic bytes, start event, end event)
+
+        @staticmethod
+        def _bytes(a, m_out, out):
+            n = a.reference_tensor().numel()
+            tot = 0
+            seen = set()
+            for t in (a.x, a.xe, a.m0, a.m1, a.m2, a.e_cond, a.e_uncond):
+                if t is not None and t.data_ptr() not in seen:
+                    seen.add(t.data_ptr())
+                    tot += n * t.element_size()
+            for t in (m_out, out):
+                if t is not None:
+                    tot += n * t.element_size()
+            return tot
+
+        def step(self, a):
+            if not self.recording:
+                return super().step(a)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m_out, out = super().step(a)
+            e1.record()
+            key = f"{FORM_NAMES[a.form]}|n_model={a.n_model}|m_out={int(m_out is not None)}"
+            self.records.append((key, self._bytes(a, m_out, out), e0, e1))
+            return m_out, out
+
+        def dynamic_threshold(self, a, q, max_val):
+            if not self.recording:
+                return super().dynamic_threshold(a, q, max_val)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s = super().dynamic_threshold(a, q, max_val)
+            e1.record()
+            n = a.reference_tensor().numel()
+            b = sum(n * t.element_size() for t in (a.xe if a.xe is not None else a.x, a.e_cond, a.e_uncond) if t is not None)
+            self.records.append((f"quantile|n_model={a.n_model}", b, e0, e1))
+            return s
+
+        def summary(self):
+            agg = {}
+            for key, b, e0, e1 in self.records:
+                d = agg.setdefault(key, {"launches": 0, "ms": 0.0, "bytes": 0})
+                d["launches"] += 1
+                d["ms"] += e0.elapsed_time(e1)
+                d["bytes"] += b
+            for d in agg.values():
+                d["avg_us"] = d["ms"] * 1e3 / d["launches"]
+                d["bytes_per_launch"] = d["bytes"] / d["launches"]
+                d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else None
+            return agg
+
+    return TimedBackend()
+
+
+def headline_kernels(be, peak, shape=(4096, 4, 64, 64), reps=30):
+    """North-star kernel timed alone: fused 3rd-order multistep update, x + 3 buffers -> x_t."""
+    from dpm_solver_b200.ops import StepArgs, FORM_MS3
+    out = {}
+    n = int(np.prod(shape))
+    for name, dt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
+        sets = []
+        for s in range(3):  # rotate through 3 buffer sets: each launch touches > L2 of fresh lines
+            sets.append([torch.randn(n, device="cuda", dtype=dt) for _ in range(4)] + [torch.empty(n, device="cuda", dtype=dt)])
+        def launch(i):
+            x, m0, m1, m2, o = sets[i % 3]
+            be.step(StepArgs(form=FORM_MS3, x=x, m0=m0, m1=m1, m2=m2, out=o, a=0.95, c0=-0.1, c1=0.05, c2=-0.01,
+                             w0=1.02, w1=0.98, w2=0.51, w3=0.5))
+        for i in range(5):
+            launch(i)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for i, (a, b) in enumerate(ev):
+            a.record(); launch(i); b.record()
+        torch.cuda.synchronize()
+        us = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+        med = us[len(us) // 2]
+        byts = 5 * n * (2 if dt == torch.bfloat16 else 4)
+        out[f"ms3_update_{name}_[4096,4,64,64]"] = {
+            "bytes_per_launch": byts, "median_us": med, "min_us": us[0], "gbs": byts / (med * 1e-6) / 1e9,
+            "frac_of_peak": byts / (med * 1e-6) / 1e9 / peak, "gelem_s": n / (med * 1e-6) / 1e9}
+        del sets
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_b200(args, w):
+    import torch.distributed as dist
+    from cases import make_betas
+    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    be = make_timed_backend()
+    ops.set_backend(be)
+    be.set_tuning(args.variant, args.threads, args.ctas)
+
+    dt = DT[w["dtype"]]
+    shape = tuple(w["shape"])
+    B = shape[0]
+    E = int(np.prod(shape))
+    kind, betas = make_betas(w["schedule"])
+    ns = NoiseScheduleVP("discrete", betas=torch.from_numpy(betas)) if kind == "discrete" else NoiseScheduleVP("linear")
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_T = torch.randn(shape, device=dev, generator=g).to(dt)
+    nb = 2 if w["cfg"] else 1
+    banks = [torch.randn((nb * B,) + shape[1:], device=dev, generator=g).to(dt) for _ in range(3)]
+    cnt = [0]
+    if w["cfg"]:
+        def net(xx, tt, cc):
+            cnt[0] += 1
+            return banks[cnt[0] % 3]
+        fn = model_wrapper(net, ns, guidance_type="classifier-free", condition=torch.ones(B, 1, device=dev),
+                           unconditional_condition=torch.zeros(B, 1, device=dev), guidance_scale=w["cfg"])
+    else:
+        def net(xx, tt):
+            cnt[0] += 1
+            return banks[cnt[0] % 3]
+        fn = model_wrapper(net, ns)
+    solver = DPM_Solver(fn, ns, algorithm_type=w["algo"], state_dtype=dt,
+                        correcting_x0_fn="dynamic_thresholding" if w["thresholding"] else None,
+                        plan_broadcast=world > 1)
+    kw = dict(steps=w["steps"], order=w["order"], method=w["method"], skip_type="time_uniform")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        y = solver.sample(x_T, **kw)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM ----
+    launches0 = be.launch_count()
+    be.recording, be.records = True, []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            y = solver.sample(x_T, **kw)
+        e1.record()
+        barrier()
+    be.recording = False
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    gpu_launches = be.launch_count() - launches0
+    ksum = be.summary()
+    value = world * E * n_updates(w) * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers, H2D of x_T and D2H of the result inside the timed region ----
+    x_host = x_T.cpu().pin_memory()
+    y_host = torch.empty_like(x_host).pin_memory()
+    for _ in range(2):
+        y_host.copy_(solver.sample(x_host.to(dev, non_blocking=True), **kw), non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        y_host.copy_(solver.sample(xd, **kw), non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e_val = world * E * n_updates(w) * args.steps / (ms_e2e * 1e-3) / 1e9
+    checksum = float(y_host.float().abs().mean())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        dom_key = max(ksum, key=lambda k: ksum[k]["ms"])
+        dom = ksum[dom_key]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom_key)
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "solver-update GElem/s", "value": value, "unit": "GElem/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_shape": list(shape), "global_batch": B * world,
+                       "parallelism": f"batch-sharded x{world}, one broadcast of the scalar plan, no tensor traffic",
+                       "l2": "per-update working set (x, eps bank, buffers: >= 4 x %.0f MB) exceeds the 126 MB L2; eps banks rotate" % (E * x_T.element_size() / 1e6),
+                       "variant": args.variant, "checksum_absmean": checksum},
+            "hbm_gbs_total": sum(d["bytes"] for d in ksum.values()) / (sum(d["ms"] for d in ksum.values()) * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["gbs"] / peak, "peak_source": peak_src, "bytes_per_launch": dom["bytes_per_launch"],
+                         "avg_us": dom["avg_us"], "launches": dom["launches"], "traffic": traffic},
+            "kernels": ksum,
+            "e2e": {"value": e2e_val, "unit": "GElem/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size() * world,
+                    "d2h_bytes_per_step": y_host.numel() * y_host.element_size() * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": gpu_launches,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_extras:
+            del y, banks
+            torch.cuda.empty_cache()
+            out["kernels_alone"] = headline_kernels(be, peak)
+            sample_batch = 64 if shape[-1] <= 64 else 4
+            val, dtc, cores = cpu_arm(w, sample_batch, repeats=1, warmup=1)
+            out["cpu_baseline"] = {"value": val, "unit": "GElem/s", "cores": cores, "kind": "port",
+                                   "sample": f"[{sample_batch},{','.join(map(str, shape[1:]))}] fp32, {w['steps']} solver steps, {dtc * 1e3:.0f} ms"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the kernel-alone and CPU-baseline legs")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -163,13 +163,17 @@ def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, gu
 class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
                  correcting_xt_fn=None, thresholding_max_val=1., dynamic_thresholding_ratio=0.995,
-                 state_dtype=None):
-        """Same arguments as the reference (:338-347) plus `state_dtype`:
+                 state_dtype=None, plan_broadcast=False):
+        """Same arguments as the reference (:338-347) plus `state_dtype` and `plan_broadcast`:
 
         state_dtype=None keeps the reference's type promotion (fp32 state and buffers even for
         bf16/fp16 inputs, because its fp32 coefficient tensors promote every update);
         state_dtype=torch.bfloat16 / torch.float16 keeps x and the buffered model values in 16-bit
         storage (fp32 arithmetic in registers, one rounding on store) and halves HBM traffic.
+
+        plan_broadcast=True (batch-sharded multi-GPU runs, torch.distributed initialised): rank 0
+        broadcasts the scalar coefficient plan once per sample() so all ranks use bit-identical
+        coefficients (distributed.py); the tensors themselves are never communicated.
         """
         self._wrapped = model_fn
         self.model = lambda x, t: model_fn(x, t.expand((x.shape[0])))
@@ -188,6 +192,13 @@ class DPM_Solver:
         if state_dtype is not None and state_dtype not in ops.SUPPORTED_DTYPES:
             raise TypeError("state_dtype must be one of {}".format(ops.SUPPORTED_DTYPES))
         self.state_dtype = state_dtype
+        self.plan_broadcast = bool(plan_broadcast)
+
+    def _sync_plan(self, coeffs):
+        if not self.plan_broadcast:
+            return coeffs
+        from .distributed import broadcast_plan
+        return broadcast_plan(coeffs)
 
     # -- small helpers ------------------------------------------------------------------------
     @property
@@ -568,7 +579,8 @@ class DPM_Solver:
                 ts = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device='cpu')
                 assert ts.shape[0] - 1 == steps
                 ts_dev = ts.to(device)
-                plan = P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order, lower_order_final)
+                plan = self._sync_plan(P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order,
+                                                        lower_order_final))
                 # model evaluation 0, then one fused launch per step:
                 #   m_{i} = convert(net(x_i, t_i));  x_{i+1} = update(x_i, m_i, m_{i-1}, m_{i-2})
                 step = 0
@@ -620,6 +632,12 @@ class DPM_Solver:
                     r1 = None if o <= 1 else (lambda_inner[1] - lambda_inner[0]) / h
                     r2 = None if o <= 2 else (lambda_inner[2] - lambda_inner[0]) / h
                     plans.append(P.singlestep_plan(ns, self.algorithm_type, solver_type, o, s, t, r1, r2))
+                if self.plan_broadcast:
+                    flat = self._sync_plan([co for sp in plans for co in sp.stages])
+                    k = 0
+                    for sp in plans:
+                        sp.stages = flat[k:k + len(sp.stages)]
+                        k += len(sp.stages)
                 all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
                 all_dev = all_times.to(device)
                 outer_dev = timesteps_outer.to(device)

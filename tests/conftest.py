@@ -52,3 +52,9 @@ def cuda_backend():
     ops.set_backend(ops.CudaBackend())
     yield ops.backend()
     ops.set_backend(old)
+
+
+@pytest.fixture()
+def oracle_backend_cpu():
+    from oracle_backend import OracleBackend
+    return OracleBackend()

@@ -1,0 +1,106 @@
+"""GPU loop parity: DPM_Solver.sample() on cuda:0 through the C-ABI against golden outputs of the
+unmodified reference (fp32: bit-identical for networks made of exact IEEE ops; <=1e-5 relative, the
+north-star tolerance, when the network itself calls sin() on the device)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import SAMPLE_CASES
+from helpers import CASES, rel_err, run_product_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # BASELINE.json north_star: "<=1e-5 relative fp32"
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in SAMPLE_CASES])
+def test_sample_matches_reference(golden, cuda_backend, name):
+    g = golden["samples"]
+    case = CASES[name]
+    before = cuda_backend.launch_count()
+    y, inter, calls = run_product_case(case, device="cuda:0")
+    assert cuda_backend.launch_count() > before, "the CUDA library did not run"
+    assert y.is_cuda and y.dtype == torch.float32
+    # identical sequence of network calls
+    np.testing.assert_allclose(np.asarray([c[0] for c in calls], dtype=np.float32), g[f"{name}/calls_t"], rtol=1e-6)
+    assert [c[1][0] for c in calls] == g[f"{name}/calls_b"].tolist()
+    if case["net"] == "exact":
+        np.testing.assert_array_equal(y.cpu().numpy(), g[f"{name}/y"])
+        if f"{name}/inter" in g:
+            for a, b in zip(inter, g[f"{name}/inter"]):
+                np.testing.assert_array_equal(a.cpu().numpy(), b)
+    else:
+        assert rel_err(y.cpu().numpy(), g[f"{name}/y"]) <= TOL
+
+
+def test_known_answers_config1(golden, cuda_backend):
+    """DPM-Solver++2M, 20 steps, [8,4,64,64], sin network."""
+    y, _, calls = run_product_case(CASES["c1_pp2m_sin"], device="cuda:0")
+    assert len(calls) == 20 and abs(calls[0][0] - 999.0) < 1e-3 and abs(calls[-1][0] - 49.95) < 1e-2
+    assert abs(float(y.mean()) - (-0.02713880)) < 1e-5
+    assert abs(float(y.abs().mean()) - 8.39973736) < 1e-4
+    ref = [-1.21692860, -5.25487947, 1.66610932]
+    assert np.allclose(y[0, 0, 0, :3].cpu().numpy(), ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["pp2m", "pp3m", "eps3s_cfg", "pp3m_thr", "pp2m_cfg_v", "pp3s_taylor"])
+@pytest.mark.parametrize("sdt", [torch.bfloat16, torch.float16])
+def test_sample_16bit_state(golden, cuda_backend, oracle_backend_cpu, name, sdt):
+    """16-bit storage (fp32 math, RN on store): bitwise equal to the numpy executor run with the
+    same storage type, and within storage precision of the fp32 reference."""
+    from dpm_solver_b200 import ops
+    case = CASES[name]
+    y, _, _ = run_product_case(case, device="cuda:0", state_dtype=sdt, model_dtype=sdt)
+    assert y.dtype == sdt
+    ops.set_backend(oracle_backend_cpu)
+    y_ref, _, _ = run_product_case(case, device="cpu", state_dtype=sdt, model_dtype=sdt)
+    if not case.get("thresholding"):
+        assert torch.equal(y.cpu(), y_ref)
+    g = golden["samples"][f"{name}/y"]
+    eps = 2 ** -8 if sdt == torch.bfloat16 else 2 ** -11
+    assert rel_err(y.float().cpu().numpy(), g) < 40 * eps
+
+
+def test_mixed_bf16_model_fp32_state(golden, cuda_backend):
+    """Reference promotion: a bf16 network output feeds an fp32 state (SURVEY 8a, bf16 note)."""
+    case = CASES["pp2m_cfg"]
+    y, _, _ = run_product_case(case, device="cuda:0", model_dtype=torch.bfloat16)
+    assert y.dtype == torch.float32
+    assert rel_err(y.cpu().numpy(), golden["samples"]["pp2m_cfg/y"]) < 0.05
+
+
+def test_inverse_round_trip(cuda_backend):
+    """sample() then inverse() returns to the start for a smooth network (independent property)."""
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    from helpers import product_schedule
+    ns = product_schedule("sd")
+    net = lambda x, t: 0.3 * x
+    s = DPM_Solver(model_wrapper(net, ns), ns, algorithm_type="dpmsolver++")
+    x = torch.randn(4, 4, 16, 16, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(0))
+    y = s.sample(x, steps=60, order=3, t_end=0.05)
+    xr = s.inverse(y, steps=60, order=3, t_start=0.05, t_end=1.0)
+    assert rel_err(xr.cpu().numpy(), x.cpu().numpy()) < 2e-3
+
+
+def test_order1_is_ddim_closed_form(cuda_backend):
+    """Order 1 == DDIM: x_t = alpha_t*x0 + sigma_t*eps with x0 from (x, eps) (analytic check)."""
+    from dpm_solver_b200 import DPM_Solver
+    from helpers import product_schedule
+    ns = product_schedule("sd")
+    eps = torch.randn(2, 4, 8, 8, device="cuda:0")
+    s = DPM_Solver(lambda x, t: eps, ns, algorithm_type="dpmsolver++")
+    x = torch.randn(2, 4, 8, 8, device="cuda:0")
+    ts, tt = torch.tensor([0.8]), torch.tensor([0.6])
+    got = s.dpm_solver_first_update(x, ts.cuda(), tt.cuda())
+    a_s, s_s, a_t, s_t = (float(v) for v in (ns.marginal_alpha(ts), ns.marginal_std(ts), ns.marginal_alpha(tt), ns.marginal_std(tt)))
+    x0 = (x - s_s * eps) / a_s
+    assert rel_err(got.cpu().numpy(), (a_t * x0 + s_t * eps).cpu().numpy()) < 1e-5
+
+
+def test_adaptive_runs(cuda_backend, capsys):
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    from helpers import product_schedule
+    ns = product_schedule("vp_linear")
+    s = DPM_Solver(model_wrapper(lambda x, t: 0.2 * x, ns), ns, algorithm_type="dpmsolver")
+    x = torch.randn(2, 3, 8, 8, device="cuda:0")
+    y = s.sample(x, method="adaptive", order=3, t_end=1e-3)
+    assert torch.isfinite(y).all() and "adaptive solver nfe" in capsys.readouterr().out
