@@ -152,10 +152,18 @@ class CudaBackend:
             if not out.is_contiguous():
                 raise ValueError("dpm_solver_b200: preallocated out must be contiguous")
             d.out = out.data_ptr()
-        with torch.cuda.device(ref.device):
-            stream = torch.cuda.current_stream(ref.device).cuda_stream
-            _lib.check(self._lib.dpm_step(C.byref(d), C.c_void_p(stream)))
+        self._launch(ref.device, self._lib.dpm_step, C.byref(d))
         return m_out, out
+
+    def _launch(self, device, fn, *args):
+        """Call a C-ABI entry on torch's current stream of `device` (device guard only if needed)."""
+        if torch.cuda.current_device() == device.index:
+            rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        else:
+            with torch.cuda.device(device):
+                rc = fn(*args, C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        if rc != 0:
+            _lib.check(rc)
 
     def dynamic_threshold(self, a: StepArgs, q: float, max_val: float) -> torch.Tensor:
         """Per-sample s_b = max(quantile(|x0_b|, q), max_val) -> fp32 [B] (one launch)."""
@@ -163,11 +171,8 @@ class CudaBackend:
         if a.per_sample <= 0 or ref.numel() % a.per_sample:
             raise ValueError("dpm_solver_b200: per_sample must divide numel")
         s = torch.empty(ref.numel() // a.per_sample, dtype=torch.float32, device=ref.device)
-        with torch.cuda.device(ref.device):
-            stream = torch.cuda.current_stream(ref.device).cuda_stream
-            _lib.check(self._lib.dpm_dynamic_threshold(C.c_void_p(s.data_ptr()), C.byref(d),
-                                                       C.c_float(q), C.c_float(max_val),
-                                                       C.c_void_p(stream)))
+        self._launch(ref.device, self._lib.dpm_dynamic_threshold, C.c_void_p(s.data_ptr()), C.byref(d),
+                     C.c_float(q), C.c_float(max_val))
         return s
 
     def launch_count(self) -> int:

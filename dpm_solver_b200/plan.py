@@ -56,21 +56,34 @@ def _f(v: Number, i: int = 0) -> float:
 
 
 class Marginals:
-    """log(alpha), alpha, sigma, lambda of a vector of times (one vectorised pass)."""
+    """log(alpha), alpha, sigma, lambda of a vector of times (one vectorised pass; the expressions
+    are those of marginal_log_mean_coeff / marginal_std / marginal_lambda / marginal_alpha,
+    :127-154, sharing the single evaluation of log(alpha))."""
 
-    def __init__(self, ns, t: torch.Tensor):
+    def __init__(self, ns, t: Optional[torch.Tensor]):
+        if t is None:
+            return
         self.t = t
         self.log_alpha = ns.marginal_log_mean_coeff(t)
-        self.sigma = ns.marginal_std(t)
-        self.lam = ns.marginal_lambda(t)
-        self.alpha = torch.exp(self.log_alpha)
+        e2 = 1. - torch.exp(2. * self.log_alpha)
+        self.sigma = torch.sqrt(e2)                           # :146
+        self.lam = self.log_alpha - 0.5 * torch.log(e2)       # :153-154
+        self.alpha = torch.exp(self.log_alpha)                # :140
+
+    def __getitem__(self, i) -> "Marginals":
+        m = Marginals(None, None)
+        m.t, m.log_alpha, m.sigma, m.lam, m.alpha = self.t[i], self.log_alpha[i], self.sigma[i], self.lam[i], self.alpha[i]
+        return m
 
 
 # ---- order 1 ----------------------------------------------------------------------------------
 
 def first_update(ns, algorithm_type: str, s: torch.Tensor, t: torch.Tensor):
     """Vectorised dpm_solver_first_update scalars (:563-588) -> tensors (a, c0)."""
-    ms, mt = Marginals(ns, s), Marginals(ns, t)
+    return _first(algorithm_type, Marginals(ns, s), Marginals(ns, t))
+
+
+def _first(algorithm_type: str, ms: Marginals, mt: Marginals):
     h = mt.lam - ms.lam
     if algorithm_type == "dpmsolver++":
         phi_1 = torch.expm1(-h)
@@ -92,7 +105,10 @@ def first_update_coeffs(ns, algorithm_type, s, t) -> Coeffs:
 
 def multistep_second(ns, algorithm_type, solver_type, t_prev_1, t_prev_0, t):
     """multistep_dpm_solver_second_update scalars (:815-851) -> tensors (a, c0, c1, inv_r0)."""
-    m1, m0, mt = Marginals(ns, t_prev_1), Marginals(ns, t_prev_0), Marginals(ns, t)
+    return _ms2(algorithm_type, solver_type, Marginals(ns, t_prev_1), Marginals(ns, t_prev_0), Marginals(ns, t))
+
+
+def _ms2(algorithm_type, solver_type, m1: Marginals, m0: Marginals, mt: Marginals):
     h_0 = m0.lam - m1.lam
     h = mt.lam - m0.lam
     r0 = h_0 / h
@@ -112,7 +128,10 @@ def multistep_second(ns, algorithm_type, solver_type, t_prev_1, t_prev_0, t):
 
 def multistep_third(ns, algorithm_type, t_prev_2, t_prev_1, t_prev_0, t):
     """multistep_dpm_solver_third_update scalars (:871-903); solver_type is ignored there."""
-    m2, m1, m0, mt = (Marginals(ns, v) for v in (t_prev_2, t_prev_1, t_prev_0, t))
+    return _ms3(algorithm_type, *(Marginals(ns, v) for v in (t_prev_2, t_prev_1, t_prev_0, t)))
+
+
+def _ms3(algorithm_type, m2: Marginals, m1: Marginals, m0: Marginals, mt: Marginals):
     h_1 = m1.lam - m2.lam
     h_0 = m0.lam - m1.lam
     h = mt.lam - m0.lam
@@ -165,29 +184,31 @@ def multistep_orders(steps: int, order: int, lower_order_final: bool) -> List[in
 
 
 def multistep_plan(ns, algorithm_type, solver_type, timesteps: torch.Tensor, order: int,
-                   lower_order_final: bool) -> List[Coeffs]:
-    """Coefficients of every update of a multistep run; plan[i] moves timesteps[i] -> [i+1]."""
+                   lower_order_final: bool, marginals: Optional[Marginals] = None) -> List[Coeffs]:
+    """Coefficients of every update of a multistep run; plan[i] moves timesteps[i] -> [i+1].
+    One vectorised evaluation of the schedule over the grid, then one vector op set per order."""
     ts = _cpu(timesteps)
     steps = ts.numel() - 1
+    M = marginals if marginals is not None else Marginals(ns, ts)
     orders = multistep_orders(steps, order, lower_order_final)
     plan: List[Optional[Coeffs]] = [None] * steps
     idx = {p: [i for i, o in enumerate(orders) if o == p] for p in (1, 2, 3)}
     if idx[1]:
         i = torch.tensor(idx[1])
-        a, c0 = first_update(ns, algorithm_type, ts[i], ts[i + 1])
+        a, c0 = (v.reshape(-1).tolist() for v in _first(algorithm_type, M[i], M[i + 1]))
         for k, j in enumerate(idx[1]):
-            plan[j] = Coeffs(FORM_LIN1, _f(a, k), _f(c0, k), order=1)
+            plan[j] = Coeffs(FORM_LIN1, a[k], c0[k], order=1)
     if idx[2]:
         i = torch.tensor(idx[2])
-        a, c0, c1, w0 = multistep_second(ns, algorithm_type, solver_type, ts[i - 1], ts[i], ts[i + 1])
+        a, c0, c1, w0 = (v.reshape(-1).tolist() for v in _ms2(algorithm_type, solver_type, M[i - 1], M[i], M[i + 1]))
         for k, j in enumerate(idx[2]):
-            plan[j] = Coeffs(FORM_DIFF2, _f(a, k), _f(c0, k), _f(c1, k), w0=_f(w0, k), order=2)
+            plan[j] = Coeffs(FORM_DIFF2, a[k], c0[k], c1[k], w0=w0[k], order=2)
     if idx[3]:
         i = torch.tensor(idx[3])
-        v = multistep_third(ns, algorithm_type, ts[i - 2], ts[i - 1], ts[i], ts[i + 1])
+        v = [u.reshape(-1).tolist() for u in _ms3(algorithm_type, M[i - 2], M[i - 1], M[i], M[i + 1])]
         for k, j in enumerate(idx[3]):
-            plan[j] = Coeffs(FORM_MS3, _f(v[0], k), _f(v[1], k), _f(v[2], k), _f(v[3], k),
-                             w0=_f(v[4], k), w1=_f(v[5], k), w2=_f(v[6], k), w3=_f(v[7], k), order=3)
+            plan[j] = Coeffs(FORM_MS3, v[0][k], v[1][k], v[2][k], v[3][k], w0=v[4][k], w1=v[5][k], w2=v[6][k],
+                             w3=v[7][k], order=3)
     return plan  # type: ignore[return-value]
 
 

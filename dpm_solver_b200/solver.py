@@ -71,8 +71,9 @@ class WrappedModel:
             return (t_continuous - 1. / self.noise_schedule.total_N) * 1000.
         return t_continuous
 
-    def _call_model(self, x, t_continuous, cond=None):
-        t_input = self.get_model_input_time(t_continuous)
+    def _call_model(self, x, t_continuous, cond=None, t_input=None):
+        if t_input is None:
+            t_input = self.get_model_input_time(t_continuous)
         if cond is None:
             return self.model(x, t_input, **self.model_kwargs)
         return self.model(x, t_input, cond, **self.model_kwargs)
@@ -87,18 +88,31 @@ class WrappedModel:
         """False only for classifier guidance (needs autograd through the user's classifier)."""
         return self.guidance_type != "classifier"
 
-    def raw(self, x, t_continuous) -> RawOutput:
-        """Run the network exactly as the reference does, return its un-combined output(s)."""
+    def input_rows(self, batch: int) -> int:
+        """Length of the time vector the network receives for a batch (doubled under CFG :327)."""
+        return 2 * batch if self.uses_cfg else batch
+
+    def _cond_in(self):
+        """cat([unconditional_condition, condition]) (:328); constant over a run, so built once."""
+        key = (id(self.unconditional_condition), id(self.condition))
+        if self._c_in is None or self._c_in[0] != key:
+            self._c_in = (key, torch.cat([self.unconditional_condition, self.condition]))
+        return self._c_in[1]
+
+    def raw(self, x, t_continuous, t_input=None) -> RawOutput:
+        """Run the network exactly as the reference does, return its un-combined output(s).
+
+        `t_input`, when given, is the precomputed model-input time vector (`input_rows(B)` long,
+        same values as get_model_input_time would produce) so that no per-call arithmetic runs."""
         param = PARAM_BY_NAME[self.model_type]
         if self.guidance_type == "uncond":
-            return RawOutput(self._call_model(x, t_continuous), None, param, 1.0)
+            return RawOutput(self._call_model(x, t_continuous, t_input=t_input), None, param, 1.0)
         if self.guidance_type == "classifier-free":
             if not self.uses_cfg:
-                return RawOutput(self._call_model(x, t_continuous, cond=self.condition), None, param, 1.0)
+                return RawOutput(self._call_model(x, t_continuous, cond=self.condition, t_input=t_input), None, param, 1.0)
             x_in = torch.cat([x] * 2)
-            t_in = torch.cat([t_continuous] * 2)
-            c_in = torch.cat([self.unconditional_condition, self.condition])
-            out_u, out_c = self._call_model(x_in, t_in, cond=c_in).chunk(2)  # uncond is the first half
+            t_in = None if t_input is not None else torch.cat([t_continuous] * 2)
+            out_u, out_c = self._call_model(x_in, t_in, cond=self._cond_in(), t_input=t_input).chunk(2)  # uncond first
             return RawOutput(out_c, out_u, param, float(self.guidance_scale))
         raise RuntimeError("raw() is not available with classifier guidance")
 
@@ -223,20 +237,30 @@ class DPM_Solver:
         return float(ns.marginal_alpha(t_host)), float(ns.marginal_std(t_host))
 
     # -- model evaluation ---------------------------------------------------------------------
-    def _evaluate(self, x, t_dev) -> RawOutput:
+    def _evaluate(self, x, t_dev, t_input=None) -> RawOutput:
         """Call the user's network at (x, t); same call the reference makes through self.model."""
         w = self._wrapped
         if isinstance(w, WrappedModel) and w.fusable:
-            return w.raw(x, t_dev.expand((x.shape[0])))
+            return w.raw(x, t_dev.expand((x.shape[0])), t_input)
         return RawOutput(self.model(x, t_dev), None, PARAM_NOISE, 1.0)
 
-    def _conv_args(self, raw: RawOutput, xe, t_host, sdtype) -> StepArgs:
-        """StepArgs fields that turn `raw` into the buffered model value at time t."""
+    def _input_times(self, t_host: torch.Tensor, batch: int, device):
+        """[n_evals, rows] device matrix of model-input times for a whole run (one tiny kernel per
+        sample() instead of two per model call); None when the model takes t_continuous itself."""
+        w = self._wrapped
+        if not (isinstance(w, WrappedModel) and w.fusable and w.noise_schedule.schedule == 'discrete'):
+            return None
+        t_in = w.get_model_input_time(t_host.reshape(-1)).to(device)     # (t - 1/N) * 1000, fp32, :278
+        return t_in[:, None].expand(t_in.shape[0], w.input_rows(batch)).contiguous()
+
+    def _conv_args(self, raw: RawOutput, xe, alsig, sdtype) -> StepArgs:
+        """StepArgs fields that turn `raw` into the buffered model value at time t.
+        `alsig` is (alpha_t, sigma_t) from the plan, or the host time tensor to derive them from."""
         a = StepArgs(n_model=2 if raw.e_uncond is not None else 1, e_cond=raw.e_cond,
                      e_uncond=raw.e_uncond, param=raw.param, guidance=raw.guidance,
                      predict_x0=self._pp, state_dtype=sdtype)
         if self._pp or raw.param != PARAM_NOISE:
-            a.alpha_e, a.sigma_e = self._alpha_sigma(t_host)
+            a.alpha_e, a.sigma_e = alsig if isinstance(alsig, tuple) else self._alpha_sigma(alsig)
             a.xe = xe
         return a
 
@@ -244,7 +268,7 @@ class DPM_Solver:
         return (self._pp or raw.e_uncond is not None or raw.param != PARAM_NOISE
                 or raw.e_cond.dtype != sdtype)
 
-    def _post_model(self, raw: RawOutput, xe, t_dev, t_host, co: Optional[P.Coeffs] = None, x=None,
+    def _post_model(self, raw: RawOutput, xe, t_dev, alsig, co: Optional[P.Coeffs] = None, x=None,
                     m1=None, m2=None, want_m: bool = True):
         """The fused post-model step: buffered value from `raw` (+ optional update `co`).
 
@@ -257,7 +281,7 @@ class DPM_Solver:
             m_new = raw.e_cond if raw.e_cond.is_contiguous() else raw.e_cond.contiguous()
             x_next = self._pure_update(co, x, m_new, m1, m2) if co is not None else None
             return m_new, x_next
-        a = self._conv_args(raw, xe, t_host, sd)
+        a = self._conv_args(raw, xe, alsig, sd)
         if self._pp and self._dynamic_thresholding:
             a.per_sample = xe.numel() // xe.shape[0]
             a.thr = be.dynamic_threshold(a, float(self.dynamic_thresholding_ratio),
@@ -401,12 +425,14 @@ class DPM_Solver:
         return x_t
 
     def _run_singlestep(self, x, sp: P.SinglestepPlan, model_s=None, model_s1=None, keep=False,
-                        times_dev: Optional[List[torch.Tensor]] = None):
+                        times_dev: Optional[List[torch.Tensor]] = None, alsig=None, t_inputs=None):
         """Execute one singlestep update: one fused launch per model evaluation.
 
         Stage j converts the network output evaluated at (x_j, times[j]) and, in the same kernel,
         produces the next intermediate state from the base state x (:630-640, :723-750)."""
         td = times_dev if times_dev is not None else [self._device_time(tt, x) for tt in sp.times]
+        als = alsig if alsig is not None else sp.times
+        tin = t_inputs if t_inputs is not None else [None] * len(sp.times)
         ms: List[Optional[torch.Tensor]] = [model_s, model_s1, None]
         taylor3 = sp.order == 3 and sp.stages[-1].form == FORM_SS3T
         xe = x
@@ -428,12 +454,12 @@ class DPM_Solver:
                 if not skip_update:
                     x_next = self._pure_update(co, x, given, m1, m2)
             else:
-                raw = self._evaluate(xe, td[j])
+                raw = self._evaluate(xe, td[j], tin[j])
                 want = keep or (not last and (j == 0 or taylor3))
                 if skip_update:
-                    m_new, _ = self._post_model(raw, xe, td[j], sp.times[j])
+                    m_new, _ = self._post_model(raw, xe, td[j], als[j])
                 else:
-                    m_new, x_next = self._post_model(raw, xe, td[j], sp.times[j], co, x, m1, m2, want_m=want)
+                    m_new, x_next = self._post_model(raw, xe, td[j], als[j], co, x, m1, m2, want_m=want)
                 ms[j] = m_new
             xe = x_next
         return x_next, ms
@@ -579,12 +605,15 @@ class DPM_Solver:
                 ts = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device='cpu')
                 assert ts.shape[0] - 1 == steps
                 ts_dev = ts.to(device)
+                marg = P.Marginals(ns, ts)
                 plan = self._sync_plan(P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order,
-                                                        lower_order_final))
+                                                        lower_order_final, marginals=marg))
                 # model evaluation 0, then one fused launch per step:
                 #   m_{i} = convert(net(x_i, t_i));  x_{i+1} = update(x_i, m_i, m_{i-1}, m_{i-2})
+                alsig = list(zip(marg.alpha.tolist(), marg.sigma.tolist()))   # (alpha_t, sigma_t) per grid point
+                tin = self._input_times(ts, x.shape[0], device)
                 step = 0
-                raw = self._evaluate(x, ts_dev[0])
+                raw = self._evaluate(x, ts_dev[0], None if tin is None else tin[0])
                 xe = x
                 if self.correcting_xt_fn is not None:
                     x = self._state_like(self.correcting_xt_fn(x, ts_dev[0], step), sd)
@@ -596,7 +625,7 @@ class DPM_Solver:
                     m1 = older[-1] if co.order >= 2 else None
                     m2 = older[-2] if co.order >= 3 else None
                     want = order >= 2 and step < steps
-                    m_new, x_new = self._post_model(raw, xe, ts_dev[step - 1], ts[step - 1:step], co, x,
+                    m_new, x_new = self._post_model(raw, xe, ts_dev[step - 1], alsig[step - 1], co, x,
                                                     m1, m2, want_m=want)
                     x = x_new
                     t = ts_dev[step]
@@ -610,7 +639,7 @@ class DPM_Solver:
                             older.pop(0)
                     # We do not need to evaluate the final model value.
                     if step < steps:
-                        raw = self._evaluate(x, t)
+                        raw = self._evaluate(x, t, None if tin is None else tin[step])
                         xe = x
             elif method in ['singlestep', 'singlestep_fixed']:
                 if method == 'singlestep':
@@ -641,12 +670,17 @@ class DPM_Solver:
                 all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
                 all_dev = all_times.to(device)
                 outer_dev = timesteps_outer.to(device)
+                marg = P.Marginals(ns, all_times)
+                alsig = list(zip(marg.alpha.tolist(), marg.sigma.tolist()))
+                tin = self._input_times(all_times, x.shape[0], device)
                 k = 0
                 step = 0
                 for step, sp in enumerate(plans):
-                    td = [all_dev[k + j:k + j + 1] for j in range(len(sp.times))]
-                    k += len(sp.times)
-                    x, _ = self._run_singlestep(x, sp, times_dev=td)
+                    nt = len(sp.times)
+                    td = [all_dev[k + j:k + j + 1] for j in range(nt)]
+                    x, _ = self._run_singlestep(x, sp, times_dev=td, alsig=alsig[k:k + nt],
+                                                t_inputs=None if tin is None else [tin[k + j] for j in range(nt)])
+                    k += nt
                     if self.correcting_xt_fn is not None:
                         x = self._state_like(self.correcting_xt_fn(x, outer_dev[step + 1], step), sd)
                     if return_intermediate:

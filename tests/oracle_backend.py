@@ -70,7 +70,7 @@ class OracleBackend:
         if a.predict_x0:
             x0 = (xe - f32(a.sigma_e) * eps) / f32(a.alpha_e)
             if thr is not None:
-                s = thr.reshape((-1,) + (1,) * (x0.ndim - 1))
+                s = np.repeat(thr.reshape(-1), a.per_sample).reshape(x0.shape)
                 x0 = np.minimum(np.maximum(x0, -s), s) / s
             return x0.astype(f32)
         return eps.astype(f32)
