@@ -124,6 +124,17 @@ static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for
   kp->guidance = d->guidance; kp->alpha_e = d->alpha_e; kp->sigma_e = d->sigma_e;
   kp->a = d->a; kp->c0 = d->c0; kp->c1 = d->c1; kp->c2 = d->c2;
   kp->w0 = d->w0; kp->w1 = d->w1; kp->w2 = d->w2; kp->w3 = d->w3; kp->w4 = d->w4;
+  // reciprocal-refinement division (common.cuh: div_const) is used when every divisor the launch
+  // can touch qualifies; host IEEE division gives the correctly rounded fp32 reciprocals
+  const bool need_alpha = d->n_model >= 1 && d->predict_x0;
+  const bool need_w4 = form == DPM_FORM_SS3T;
+  bool ok = true;
+  if (need_alpha) ok = ok && recip_div_ok(d->alpha_e);
+  if (need_w4) ok = ok && recip_div_ok(d->w4);
+  kp->r_alpha = need_alpha && ok ? 1.0f / d->alpha_e : 0.f;
+  kp->r_sigma = 0.f;
+  kp->r_w4 = need_w4 && ok ? 1.0f / d->w4 : 0.f;
+  kp->fast_div = ok ? 1 : 0;
   return DPM_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "dpm_solver_b200.h"
 
@@ -45,6 +46,10 @@ struct KParams {
   float guidance, alpha_e, sigma_e;
   float a, c0, c1, c2;
   float w0, w1, w2, w3, w4;
+  // correctly rounded reciprocals of the kernel-constant divisors (host computed) and a flag telling
+  // the device that the reciprocal-refinement division below is valid for all three of them
+  float r_alpha, r_sigma, r_w4;
+  int32_t fast_div;
 };
 
 // ---- storage types ------------------------------------------------------------------------
@@ -188,6 +193,59 @@ __device__ __forceinline__ float round_any(int dt, float v) {
   }
 }
 
+// ---- exact division by a launch constant -------------------------------------------------------
+// x / d for a divisor that is uniform over the launch, without the per-element IEEE division
+// subroutine (MUFU.RCP + 4 FFMA + FCHK + slow-path call). With r = RN(1/d) prepared once:
+//   q0 = RN(x*r); e = x - q0*d (exact, one FMA); q1 = RN(q0 + e*r); repeat once.
+// q0 is within 2 ulp of x/d, each refinement with the exact residual contracts the error below
+// half an ulp, and a second pass leaves a correctly rounded quotient unchanged (Markstein's
+// division theorem; it needs d's significand not to be all ones -- checked on the host -- and no
+// underflow/overflow in the residual, guarded below by routing tiny/huge/non-finite x to the IEEE
+// division). tests/test_gpu_kernels.py::test_constant_division_is_ieee compares it bit for bit
+// with true division over ~10^9 (x, d) pairs. Explicit fmaf() stays fused under -fmad=false.
+__device__ __forceinline__ float div_const(float x, float d, float r) {
+  float q = x * r;
+  float e = fmaf(-q, d, x);
+  q = fmaf(e, r, q);
+  e = fmaf(-q, d, x);
+  q = fmaf(e, r, q);
+  const float ax = fabsf(x);
+  if (!(ax > 1e-30f && ax < 1e30f)) q = x / d;  // zero, denormal-range, huge, inf, nan: IEEE path
+  return q;
+}
+// packet form: one range guard (and one cold IEEE block) per 8 elements instead of per element
+__device__ __forceinline__ void div_const8(float (&x)[8], float d, float r) {
+  float q[8];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = x[i] * r;
+    float e = fmaf(-t, d, x[i]);
+    t = fmaf(e, r, t);
+    e = fmaf(-t, d, x[i]);
+    q[i] = fmaf(e, r, t);
+    const float ax = fabsf(x[i]);
+    bad |= !(ax > 1e-30f && ax < 1e30f);
+  }
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = x[i] / d;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = q[i];
+}
+__host__ __device__ __forceinline__ bool recip_div_ok(float d) {
+  // normal, finite, not too extreme, significand not all ones
+#ifdef __CUDA_ARCH__
+  const uint32_t b = __float_as_uint(d);
+#else
+  uint32_t b;
+  memcpy(&b, &d, 4);
+#endif
+  const uint32_t ex = (b >> 23) & 0xffu;
+  return ex > 40u && ex < 210u && (b & 0x7fffffu) != 0x7fffffu;
+}
+
 // ---- per-element arithmetic -----------------------------------------------------------------
 // model_wrapper.noise_pred_fn :288-298
 __device__ __forceinline__ float convert_param(int param, float out, float xe, float alpha,
@@ -217,6 +275,57 @@ __device__ __forceinline__ float model_value(const KParams& p, float xe, float e
   return eps;
 }
 
+// Same computation for a packet of 8 elements, with the launch-uniform switches hoisted out of
+// the element loop (hand loop-unswitching): noise-parameterised networks -- the common case --
+// run straight-line code; everything else takes the generic per-element function above.
+// `thr8` is only read when clamp is set.
+template <int NE>
+__device__ __forceinline__ void model_values8(const KParams& p, const float (&xe)[8],
+                                              const float (&ec)[8], const float (&eu)[8],
+                                              const float (&thr8)[8], bool clamp, bool thr_uniform,
+                                              float (&T)[8]) {
+  if (p.fast_div && p.param == DPM_PARAM_NOISE && (!clamp || thr_uniform)) {
+    float eps[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) eps[i] = (NE == 2) ? eu[i] + p.guidance * (ec[i] - eu[i]) : ec[i];  // :330
+    if (!p.predict_x0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) T[i] = eps[i];
+      return;
+    }
+    float x0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x0[i] = xe[i] - p.sigma_e * eps[i];
+    div_const8(x0, p.alpha_e, p.r_alpha);  // :439
+    if (clamp) {
+      const float s = thr8[0];
+      if (recip_div_ok(s)) {
+        const float rs = __frcp_rn(s);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x0[i] = fminf(fmaxf(x0[i], -s), s);
+        div_const8(x0, s, rs);  // :424
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x0[i] = fminf(fmaxf(x0[i], -s), s) / s;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[i] = x0[i];
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) T[i] = model_value<NE>(p, xe[i], ec[i], NE == 2 ? eu[i] : 0.f, thr8[i], clamp);
+}
+
+// round a packet to its storage type once: returns the packed words and rewrites f[] with the
+// values as they will read back (so fused and unfused paths agree bit for bit)
+__device__ __forceinline__ void round_pack(Raw<float>& r, float (&f)[8]) { pack(r, f); }
+template <typename T16>
+__device__ __forceinline__ void round_pack(Raw<T16>& r, float (&f)[8]) {
+  pack(r, f);
+  unpack(r, f);
+}
+
 // the update. T0 = newest model value, m1/m2 = older buffers.
 template <int FORM>
 __device__ __forceinline__ float update_value(const KParams& p, float x, float T0, float m1,
@@ -242,8 +351,9 @@ __device__ __forceinline__ float update_value(const KParams& p, float x, float T
     // m2 = model_s, m1 = model_s1, T0 = model_s2
     float D10 = p.w0 * (m1 - m2);                 // :741
     float D11 = p.w1 * (T0 - m2);                 // :742
-    float D1 = (p.w2 * D10 - p.w3 * D11) / p.w4;  // :743
-    float D2 = (2.f * (D11 - D10)) / p.w4;        // :744
+    float n1 = p.w2 * D10 - p.w3 * D11, n2 = 2.f * (D11 - D10);
+    float D1 = p.fast_div ? div_const(n1, p.w4, p.r_w4) : n1 / p.w4;  // :743
+    float D2 = p.fast_div ? div_const(n2, p.w4, p.r_w4) : n2 / p.w4;  // :744
     return ((p.a * x + p.c0 * m2) + p.c1 * D1) + p.c2 * D2;  // :745-750 / :784-789
   }
   return 0.f;

@@ -78,22 +78,29 @@ __global__ void __launch_bounds__(kMaxThreads)
 #pragma unroll
             for (int i = 0; i < 8; ++i) fxe[i] = 0.f;
           }
-          float thr_pk = 1.f;
-          if (clamp && p.pk_per_sample)
-            thr_pk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
+          float thr8[8];
+          const bool thr_uniform = p.pk_per_sample != 0;
+          if (clamp) {
+            if (thr_uniform) {
+              const float tpk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float thr = thr_pk;
-            if (clamp && !p.pk_per_sample)
-              thr = __ldg(p.thr + (e + i) / p.per_sample);
-            float mv = model_value<NE>(p, fxe[i], fec[i], NE == 2 ? feu[i] : 0.f, thr, clamp);
-            fT[i] = round_storage<TS>(mv);
+              for (int i = 0; i < 8; ++i) thr8[i] = tpk;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) thr8[i] = __ldg(p.thr + (e + i) / p.per_sample);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) thr8[i] = 1.f;
           }
-          if (gmo != nullptr) {
-            Raw<TS> rmo;
-            pack(rmo, fT);
-            stg_pk(gmo + e, rmo);
+          if (NE != 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) feu[i] = 0.f;
           }
+          model_values8<NE>(p, fxe, fec, feu, thr8, clamp, thr_uniform, fT);
+          Raw<TS> rmo;
+          round_pack(rmo, fT);
+          if (gmo != nullptr) stg_pk(gmo + e, rmo);
         } else {
           unpack(rm0[u], fT);
         }

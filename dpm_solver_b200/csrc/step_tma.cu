@@ -157,16 +157,28 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
           { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.ec) + le); unpack(r, fec); }
           if (NE == 2) { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.eu) + le); unpack(r, feu); }
           const uint64_t pk = e0 / kPacket + lp;
-          float thr_pk = 1.f;
-          if (clamp && p.pk_per_sample) thr_pk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
+          float thr8[8], fxe[8];
+          const bool thr_uniform = p.pk_per_sample != 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float thr = thr_pk;
-            if (clamp && !p.pk_per_sample) thr = __ldg(p.thr + (e0 + le + i) / p.per_sample);
-            float mv = model_value<NE>(p, has_x ? fx[i] : 0.f, fec[i], NE == 2 ? feu[i] : 0.f, thr, clamp);
-            fT[i] = round_storage<TS>(mv);
+            thr8[i] = 1.f;
+            fxe[i] = has_x ? fx[i] : 0.f;
+            if (NE != 2) feu[i] = 0.f;
           }
-          if (has_mo) { Raw<TS> r; pack(r, fT); sts_pk(reinterpret_cast<TS*>(st + L.mo) + le, r); }
+          if (clamp) {
+            if (thr_uniform) {
+              const float tpk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) thr8[i] = tpk;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) thr8[i] = __ldg(p.thr + (e0 + le + i) / p.per_sample);
+            }
+          }
+          model_values8<NE>(p, fxe, fec, feu, thr8, clamp, thr_uniform, fT);
+          Raw<TS> rmo;
+          round_pack(rmo, fT);
+          if (has_mo) sts_pk(reinterpret_cast<TS*>(st + L.mo) + le, rmo);
         } else {
           Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m0) + le); unpack(r, fT);
         }

@@ -303,3 +303,40 @@ def test_cuda_graph_capture(cuda_backend):
     gph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_constant_division_is_ieee(cuda_backend):
+    """The reciprocal-refinement division by a launch constant (common.cuh: div_const) must equal
+    IEEE division bit for bit: ~1e9 (x, d) pairs -- random magnitudes over 60 binades, values
+    next to powers of two, exact multiples, zeros / denormals / huge values (guarded IEEE path)."""
+    n = 1 << 22
+    g = torch.Generator(device=DEV).manual_seed(7)
+    mant = torch.rand(n, device=DEV, generator=g) + 1.0
+    expo = torch.randint(-30, 30, (n,), device=DEV, generator=g).float()
+    sign = torch.randint(0, 2, (n,), device=DEV, generator=g).float() * 2 - 1
+    x = (sign * mant * torch.exp2(expo)).contiguous()
+    special = torch.tensor([0.0, -0.0, 1e-38, -1e-39, 1e-45, 3e38, -3e38, 1.0, 2.0, 0.5, 1.0000001, 0.99999994],
+                           device=DEV)
+    x[:special.numel()] = special
+    zeros = torch.zeros_like(x)
+    rs = np.random.RandomState(3)
+    divisors = np.concatenate([rs.uniform(1e-3, 1.0, 150), rs.uniform(1.0, 40.0, 40),
+                               [1.0, 0.5, 0.25, 2.0, 0.99999994, 1.0000001, 0.0029151, 0.9998, 0.33333334,
+                                np.float32(1) - np.float32(2 ** -24), 1.9999999]]).astype(np.float32)
+    xe = x.cpu().numpy()
+    bad = 0
+    for d in divisors:
+        a = StepArgs(form=FORM_NONE, n_model=1, e_cond=zeros, xe=x, predict_x0=True, alpha_e=float(d), sigma_e=0.0,
+                     state_dtype=torch.float32)
+        got = cuda_backend.step(a)[0].cpu().numpy()
+        with np.errstate(all="ignore"):
+            ref = (xe - np.float32(0.0) * np.float32(0.0)) / d
+        bad += int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+        # multiples of d divide exactly
+        xm = (x * float(d)).contiguous()
+        a.xe = xm
+        got = cuda_backend.step(a)[0].cpu().numpy()
+        with np.errstate(all="ignore"):
+            ref = xm.cpu().numpy() / d
+        bad += int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+    assert bad == 0
