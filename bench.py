@@ -449,7 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=2, help="0 direct, 1 TMA ring, 2 auto")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip the kernel-alone and CPU-baseline legs")

@@ -10,7 +10,7 @@ namespace dpm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_variant{0}, g_threads{0}, g_ctas{0};
+static std::atomic<int> g_variant{2}, g_threads{0}, g_ctas{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -186,7 +186,9 @@ static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   bool body_done = false;
   if (p.npk > 0 && all_aligned(p, nd)) {
     int r = 1;
-    if (t.variant == 1) r = launch_step_tma(p, t, stream);
+    // small launches (a few tiles per SM) gain nothing from the ring; auto keeps them direct
+    const bool tma = t.variant == 1 || (t.variant == 2 && p.npk >= (uint32_t)sm_count() * 1024u);
+    if (tma) r = launch_step_tma(p, t, stream);
     if (r == 1) r = launch_step_direct(p, t, stream);
     if (r < 0 || r > 1) return r;
     body_done = (r == 0);
@@ -211,7 +213,7 @@ const char* dpm_last_error(void) { return g_err; }
 uint64_t dpm_launch_count(void) { return g_launches.load(); }
 
 int dpm_set_tuning(int variant, int threads, int ctas_per_sm) {
-  if (variant < 0 || variant > 1) { set_error("variant must be 0 or 1"); return DPM_ERR_ARG; }
+  if (variant < 0 || variant > 2) { set_error("variant must be 0 (direct), 1 (TMA ring) or 2 (auto)"); return DPM_ERR_ARG; }
   if (threads != 0 && (threads < 32 || threads > 512 || threads % 32)) { set_error("threads must be a multiple of 32 in [32,512]"); return DPM_ERR_ARG; }
   if (ctas_per_sm < 0 || ctas_per_sm > 32) { set_error("ctas_per_sm must be in [0,32]"); return DPM_ERR_ARG; }
   g_variant = variant; g_threads = threads; g_ctas = ctas_per_sm;

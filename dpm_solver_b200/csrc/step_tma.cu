@@ -74,7 +74,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // byte offsets of the per-stream tile buffers inside one stage
 struct StageLayout {
-  uint32_t x, ec, eu, m0, m1, m2, mo, o;  // 0xffffffff = stream absent
+  uint32_t x, xe, ec, eu, m0, m1, m2, mo, o;  // 0xffffffff = stream absent
   uint32_t bytes;                          // stage size
 };
 
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   const uint32_t tile_el = tile_pk * kPacket;
   const uint32_t ntiles = (p.npk + tile_pk - 1) / tile_pk;
   const bool has_x = Needs::kX || (NE > 0 && p.use_xe);  // state slot: x, or xe when no update
+  const bool sep_xe = (NE > 0) && p.use_xe && Needs::kX && !p.xe_is_x;  // extra slot: evaluation state
   const bool clamp = (NE > 0) && (p.thr != nullptr);
   const bool has_mo = (NE > 0) && (p.m_out != nullptr);
   const char* gstate = static_cast<const char*>(Needs::kX ? p.x : p.xe);
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
     unsigned char* st = ring + (size_t)s * L.bytes;
     uint32_t tx = 0;
     if (has_x) tx += bs;
+    if (sep_xe) tx += bs;
     if (NE >= 1) tx += bm;
     if (NE == 2) tx += bm;
     if (NE == 0) tx += bs;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
     if (Needs::kM2) tx += bs;
     mbar_expect_tx(&full[s], tx);
     if (has_x) bulk_g2s(st + L.x, gstate + e0 * Traits<TS>::kBytes, bs, &full[s]);
+    if (sep_xe) bulk_g2s(st + L.xe, static_cast<const char*>(p.xe) + e0 * Traits<TS>::kBytes, bs, &full[s]);
     if (NE >= 1) bulk_g2s(st + L.ec, static_cast<const char*>(p.ec) + e0 * Traits<TE>::kBytes, bm, &full[s]);
     if (NE == 2) bulk_g2s(st + L.eu, static_cast<const char*>(p.eu) + e0 * Traits<TE>::kBytes, bm, &full[s]);
     if (NE == 0) bulk_g2s(st + L.m0, static_cast<const char*>(p.m0) + e0 * Traits<TS>::kBytes, bs, &full[s]);
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
             fxe[i] = has_x ? fx[i] : 0.f;
             if (NE != 2) feu[i] = 0.f;
           }
+          if (sep_xe) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.xe) + le); unpack(r, fxe); }
           if (clamp) {
             if (thr_uniform) {
               const float tpk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
@@ -212,10 +216,13 @@ static TmaKernel tma_form(int form) {
   switch (form) {
     case DPM_FORM_NONE: return NE > 0 ? k_step_tma<TE, TS, NE, DPM_FORM_NONE> : nullptr;
     case DPM_FORM_LIN1: return k_step_tma<TE, TS, NE, DPM_FORM_LIN1>;
+    case DPM_FORM_LIN2: return k_step_tma<TE, TS, NE, DPM_FORM_LIN2>;
+    case DPM_FORM_LIN3: return k_step_tma<TE, TS, NE, DPM_FORM_LIN3>;
     case DPM_FORM_DIFF2: return k_step_tma<TE, TS, NE, DPM_FORM_DIFF2>;
     case DPM_FORM_MS3: return k_step_tma<TE, TS, NE, DPM_FORM_MS3>;
+    case DPM_FORM_SS3T: return k_step_tma<TE, TS, NE, DPM_FORM_SS3T>;
   }
-  return nullptr;  // LIN2/LIN3/SS3T: direct variant
+  return nullptr;
 }
 template <typename TE, typename TS>
 static TmaKernel tma_ne(int ne, int form) {
@@ -229,44 +236,55 @@ static TmaKernel pick_tma(int md, int sd, int ne, int form) {
   if (ne == 0) {
     if (sd == DPM_F32) return tma_form<float, float, 0>(form);
     if (sd == DPM_BF16) return tma_form<__nv_bfloat16, __nv_bfloat16, 0>(form);
+    if (sd == DPM_F16) return tma_form<__half, __half, 0>(form);
     return nullptr;
   }
   if (md == DPM_F32 && sd == DPM_F32) return tma_ne<float, float>(ne, form);
   if (md == DPM_BF16 && sd == DPM_BF16) return tma_ne<__nv_bfloat16, __nv_bfloat16>(ne, form);
+  if (md == DPM_F16 && sd == DPM_F16) return tma_ne<__half, __half>(ne, form);
   if (md == DPM_BF16 && sd == DPM_F32) return tma_ne<__nv_bfloat16, float>(ne, form);
+  if (md == DPM_F16 && sd == DPM_F32) return tma_ne<__half, float>(ne, form);
   return nullptr;
 }
 
 int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const bool need_x = p.form != DPM_FORM_NONE;
-  if (p.n_model > 0 && p.use_xe && need_x && !p.xe_is_x) return 1;  // separate xe: direct variant
   TmaKernel k = pick_tma(p.model_dtype, p.state_dtype, p.n_model, p.form);
   if (k == nullptr) return 1;
-  const int threads = t.threads > 0 ? t.threads : 256;
-  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : 1;
-  const uint32_t tile_el = (uint32_t)threads * kTmaUnroll * kPacket;
+  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : 2;
   const uint32_t ss = p.state_dtype == DPM_F32 ? 4 : 2, ms = p.model_dtype == DPM_F32 ? 4 : 2;
-
-  StageLayout L;
-  uint32_t o = 0;
-  auto take = [&](bool on, uint32_t es) { uint32_t r = 0xffffffffu; if (on) { r = o; o += tile_el * es; } return r; };
-  const bool m1 = p.form == DPM_FORM_DIFF2 || p.form == DPM_FORM_MS3;
-  const bool m2 = p.form == DPM_FORM_MS3;
-  L.x = take(need_x || (p.n_model > 0 && p.use_xe), ss);
-  L.ec = take(p.n_model >= 1, ms);
-  L.eu = take(p.n_model == 2, ms);
-  L.m0 = take(p.n_model == 0, ss);
-  L.m1 = take(m1, ss);
-  L.m2 = take(m2, ss);
-  L.mo = take(p.n_model > 0 && p.m_out != nullptr, ss);
-  L.o = take(need_x, ss);
-  L.bytes = o;
-
+  const bool sep_xe = p.n_model > 0 && p.use_xe && need_x && !p.xe_is_x;
+  const bool m1 = p.form == DPM_FORM_LIN2 || p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_DIFF2 ||
+                  p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
+  const bool m2 = p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
   // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
   const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
-  size_t budget = per_cta < (size_t)max_smem_optin() ? per_cta : (size_t)max_smem_optin();
-  int stages = (int)((budget - 128) / L.bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  const size_t budget = per_cta < (size_t)max_smem_optin() ? per_cta : (size_t)max_smem_optin();
+
+  StageLayout L;
+  int threads = 0, stages = 0;
+  // tile = threads * kTmaUnroll packets; default: the largest tile that still leaves >= 3 stages
+  const int cand[4] = {t.threads > 0 ? t.threads : 256, 128, 64, 32};
+  for (int c = 0; c < (t.threads > 0 ? 1 : 4); ++c) {
+    const uint32_t tile_el = (uint32_t)cand[c] * kTmaUnroll * kPacket;
+    uint32_t o = 0;
+    auto take = [&](bool on, uint32_t es) { uint32_t r = 0xffffffffu; if (on) { r = o; o += tile_el * es; } return r; };
+    L.x = take(need_x || (p.n_model > 0 && p.use_xe), ss);
+    L.xe = take(sep_xe, ss);
+    L.ec = take(p.n_model >= 1, ms);
+    L.eu = take(p.n_model == 2, ms);
+    L.m0 = take(p.n_model == 0, ss);
+    L.m1 = take(m1, ss);
+    L.m2 = take(m2, ss);
+    L.mo = take(p.n_model > 0 && p.m_out != nullptr, ss);
+    L.o = take(need_x, ss);
+    L.bytes = o;
+    int st = (int)((budget - 128) / L.bytes);
+    if (st > kMaxStages) st = kMaxStages;
+    threads = cand[c];
+    stages = st;
+    if (st >= 3) break;
+  }
   if (stages < 2) return 1;
   const size_t smem = 128 + (size_t)stages * L.bytes;
 

@@ -178,7 +178,7 @@ class CudaBackend:
     def launch_count(self) -> int:
         return int(self._lib.dpm_launch_count())
 
-    def set_tuning(self, variant: int = 0, threads: int = 0, ctas_per_sm: int = 0) -> None:
+    def set_tuning(self, variant: int = 2, threads: int = 0, ctas_per_sm: int = 0) -> None:
         _lib.check(self._lib.dpm_set_tuning(variant, threads, ctas_per_sm))
 
 

@@ -43,10 +43,10 @@ def test_argument_validation_needs_no_gpu():
     assert L.dpm_step(C.byref(d), None) == -1          # tensors missing
     d.state_dtype = 7
     assert L.dpm_step(C.byref(d), None) == -1          # bad dtype
-    assert L.dpm_set_tuning(0, 96, 4) == 0 and L.dpm_set_tuning(0, 0, 0) == 0
+    assert L.dpm_set_tuning(0, 96, 4) == 0 and L.dpm_set_tuning(2, 0, 0) == 0
     v, t, c = C.c_int(), C.c_int(), C.c_int()
     L.dpm_get_tuning(C.byref(v), C.byref(t), C.byref(c))
-    assert (v.value, t.value, c.value) == (0, 0, 0)
+    assert (v.value, t.value, c.value) == (2, 0, 0)
 
 
 def test_struct_layout_matches_header():

@@ -132,19 +132,21 @@ def test_in_place_alias(cuda_backend):
     assert torch.equal(x, ref)
 
 
-@pytest.mark.parametrize("sdt,mdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("sdt,mdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
+                                     (torch.float16, torch.float16)])
 def test_tma_variant_equals_direct(cuda_backend, sdt, mdt):
     """variant 1 (cp.async.bulk shared-memory ring) must be bitwise identical to variant 0."""
     n = 8 * (148 * 512 * 3 + 77) + 4
-    cases = [make_args(f, 0, n, sdt, sdt, seed=f) for f in (FORM_LIN1, FORM_DIFF2, FORM_MS3)]
+    cases = [make_args(f, 0, n, sdt, sdt, seed=f) for f in FORMS]
     cases += [make_args(f, nm, n, sdt, mdt, predict_x0=True, seed=f + nm) for f in (FORM_NONE, FORM_LIN1, FORM_DIFF2, FORM_MS3) for nm in (1, 2)]
+    cases += [make_args(f, 2, n, sdt, mdt, predict_x0=True, sep_xe=True, param=PARAM_V, seed=f) for f in (FORM_DIFF2, FORM_SS3T, FORM_LIN3)]
     thr = torch.tensor(np.linspace(0.5, 2.0, 4), dtype=torch.float32)
     cases.append(make_args(FORM_MS3, 1, 8 * 4096, sdt, mdt, predict_x0=True, thr=thr, per_sample=8 * 1024, seed=5))
     for a in cases:
         d = to_dev(a)
         cuda_backend.set_tuning(0, 0, 0)
         m0, o0 = cuda_backend.step(d)
-        for threads, ctas in ((256, 1), (128, 2), (512, 1)):
+        for threads, ctas in ((256, 1), (128, 2), (512, 1), (0, 0)):
             cuda_backend.set_tuning(1, threads, ctas)
             m1, o1 = cuda_backend.step(d)
             torch.cuda.synchronize()
@@ -152,7 +154,7 @@ def test_tma_variant_equals_direct(cuda_backend, sdt, mdt):
                 assert (p is None) == (q is None)
                 if p is not None:
                     assert torch.equal(p, q)
-    cuda_backend.set_tuning(0, 0, 0)
+    cuda_backend.set_tuning(2, 0, 0)
 
 
 @pytest.mark.parametrize("threads,ctas", [(128, 4), (256, 8), (512, 2), (64, 16)])
@@ -162,7 +164,7 @@ def test_direct_tuning_is_result_invariant(cuda_backend, threads, ctas):
     m0, o0 = cuda_backend.step(a)
     cuda_backend.set_tuning(0, threads, ctas)
     m1, o1 = cuda_backend.step(a)
-    cuda_backend.set_tuning(0, 0, 0)
+    cuda_backend.set_tuning(2, 0, 0)
     assert torch.equal(m0, m1) and torch.equal(o0, o1)
 
 
@@ -268,6 +270,7 @@ def test_error_reporting(cuda_backend):
     assert L.dpm_step(C.byref(d), None) == -1
     assert L.dpm_lincomb(None, None, None, None, None, 4, 1., 1., 1., 1., 8, 0, None) == -1
     assert L.dpm_set_tuning(3, 0, 0) == -1 and L.dpm_set_tuning(0, 100, 0) == -1
+    assert L.dpm_set_tuning(2, 0, 0) == 0
     with pytest.raises(RuntimeError, match="CUDA-only"):
         ops.lincomb(torch.randn(8), [torch.randn(8)], 1.0, [1.0])
     with pytest.raises(TypeError):

@@ -85,7 +85,7 @@ def main():
     ap.add_argument("--n-model", type=int, default=0)
     ap.add_argument("--no-m-out", action="store_true")
     ap.add_argument("--shape", default="4096,4,64,64")
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--reps", type=int, default=30)
@@ -111,13 +111,14 @@ def main():
         return
     rows = []
     cases = [("ms3", 0, "bf16", True), ("ms3", 0, "f32", True), ("diff2", 1, "bf16", True), ("diff2", 2, "bf16", True),
-             ("ms3", 1, "f32", True), ("lin1", 0, "bf16", True)]
+             ("ms3", 1, "f32", True), ("ms3", 2, "bf16", True), ("lin1", 1, "bf16", True), ("diff2", 1, "f32", True),
+             ("none", 2, "bf16", True)]
     for form, nm, dt, mo in cases:
         sets = build(form, nm, DT[dt], DT[dt], n, m_out=mo)
         b = algo_bytes(sets[0])
         for variant, threads, ctas in itertools.chain(
-                itertools.product([0], [128, 256, 512], [2, 4, 8, 16]),
-                itertools.product([1], [128, 256, 512], [1, 2])):
+                itertools.product([0], [128, 256, 512], [2, 4, 8]),
+                itertools.product([1], [128, 256, 512], [1, 2, 3, 4])):
             if threads * ctas > 2048:
                 continue
             be.set_tuning(variant, threads, ctas)
@@ -127,7 +128,7 @@ def main():
             print(json.dumps(rows[-1]), flush=True)
         del sets
         torch.cuda.empty_cache()
-    be.set_tuning(0, 0, 0)
+    be.set_tuning(2, 0, 0)
 
 
 if __name__ == "__main__":
