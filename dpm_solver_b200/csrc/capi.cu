@@ -1,5 +1,8 @@
 // capi.cu -- the C-ABI of libdpmsolver_b200.so (see include/dpm_solver_b200.h)
 #include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -44,6 +47,25 @@ int max_smem_optin() {
     cache[dev] = v;
   }
   return cache[dev];
+}
+
+int ensure_max_smem(const void* kernel, bool nonportable_cluster) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({dev, kernel})) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
+  if (e == cudaSuccess && nonportable_cluster)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) {
+    set_error("shared-memory opt-in failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  done.insert({dev, kernel});
+  return 0;
 }
 
 static inline int esize(int dt) { return dt == DPM_F32 ? 4 : 2; }
@@ -187,7 +209,10 @@ static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   if (p.npk > 0 && all_aligned(p, nd)) {
     int r = 1;
     // small launches (a few tiles per SM) gain nothing from the ring; auto keeps them direct
-    const bool tma = t.variant == 1 || (t.variant == 2 && p.npk >= (uint32_t)sm_count() * 1024u);
+    // fp32 state: direct 256-bit loads sit at the HBM roofline already (fewer instructions per
+    // byte); 16-bit state is issue-limited there and gains 10-20% from the ring (profiles/)
+    const bool tma = t.variant == 1 || (t.variant == 2 && p.state_dtype != DPM_F32 &&
+                                         p.npk >= (uint32_t)sm_count() * 1024u);
     if (tma) r = launch_step_tma(p, t, stream);
     if (r == 1) r = launch_step_direct(p, t, stream);
     if (r < 0 || r > 1) return r;

@@ -16,6 +16,9 @@ struct Tuning {
 int sm_count();                     // SMs of the current device (cached per device)
 int max_smem_optin();               // max opt-in dynamic shared memory per CTA
 void count_launch();                // bump the library launch counter
+// opt the kernel into the device's maximum dynamic shared memory (and, optionally, non-portable
+// cluster sizes) the first time it is used on the current device; later calls are a hash lookup
+int ensure_max_smem(const void* kernel, bool nonportable_cluster = false);
 void set_error(const char* fmt, ...);
 
 // each returns 0 on launch, 1 if this variant does not serve the request, <0 / cudaError on error

@@ -294,12 +294,9 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
   if (slice > 0xffffffffull) { set_error("per_sample too large"); return DPM_ERR_UNSUPPORTED; }
 
   const size_t smem = fixed + (size_t)cap * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("quantile: smem opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
-  if (cs > 8) {
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) { set_error("quantile: cluster 16 not allowed: %s", cudaGetErrorString(e)); return (int)e; }
-  }
+  int rc = ensure_max_smem(reinterpret_cast<const void*>(k), /*nonportable_cluster=*/true);
+  if (rc != 0) return rc;
+  cudaError_t e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(n_samples * cs), 1, 1);

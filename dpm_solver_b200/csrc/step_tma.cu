@@ -293,8 +293,8 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const uint64_t cap = (uint64_t)sm_count() * ctas;
   const uint32_t grid = (uint32_t)(ntiles < cap ? ntiles : cap);
   if (grid == 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("tma: smem opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+  int rc = ensure_max_smem(reinterpret_cast<const void*>(k));  // once per kernel and device
+  if (rc != 0) return rc;
   k<<<grid, threads, smem, stream>>>(p, L, stages);
   count_launch();
   return 0;

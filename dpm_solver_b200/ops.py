@@ -68,6 +68,12 @@ class StepArgs:
         raise ValueError("StepArgs without tensors")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+if _raw_stream is None:  # older torch: go through the Stream object
+    def _raw_stream(idx):
+        return torch.cuda.current_stream(idx).cuda_stream
+
+
 class CudaBackend:
     """Executes StepArgs through libdpmsolver_b200.so."""
 
@@ -157,11 +163,12 @@ class CudaBackend:
 
     def _launch(self, device, fn, *args):
         """Call a C-ABI entry on torch's current stream of `device` (device guard only if needed)."""
-        if torch.cuda.current_device() == device.index:
-            rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        idx = device.index
+        if torch.cuda.current_device() == idx:
+            rc = fn(*args, C.c_void_p(_raw_stream(idx)))
         else:
             with torch.cuda.device(device):
-                rc = fn(*args, C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+                rc = fn(*args, C.c_void_p(_raw_stream(idx)))
         if rc != 0:
             _lib.check(rc)
 

@@ -244,13 +244,21 @@ class DPM_Solver:
             return w.raw(x, t_dev.expand((x.shape[0])), t_input)
         return RawOutput(self.model(x, t_dev), None, PARAM_NOISE, 1.0)
 
+    @staticmethod
+    def _upload(t_host: torch.Tensor, device):
+        """Host vector -> device without draining the stream (pinned staging, async copy)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            return t_host.to(device)
+        return t_host.pin_memory().to(device, non_blocking=True)
+
     def _input_times(self, t_host: torch.Tensor, batch: int, device):
         """[n_evals, rows] device matrix of model-input times for a whole run (one tiny kernel per
         sample() instead of two per model call); None when the model takes t_continuous itself."""
         w = self._wrapped
         if not (isinstance(w, WrappedModel) and w.fusable and w.noise_schedule.schedule == 'discrete'):
             return None
-        t_in = w.get_model_input_time(t_host.reshape(-1)).to(device)     # (t - 1/N) * 1000, fp32, :278
+        t_in = self._upload(w.get_model_input_time(t_host.reshape(-1)), device)   # (t - 1/N) * 1000, fp32, :278
         return t_in[:, None].expand(t_in.shape[0], w.input_rows(batch)).contiguous()
 
     def _conv_args(self, raw: RawOutput, xe, alsig, sdtype) -> StepArgs:
@@ -604,7 +612,7 @@ class DPM_Solver:
                     raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
                 ts = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device='cpu')
                 assert ts.shape[0] - 1 == steps
-                ts_dev = ts.to(device)
+                ts_dev = self._upload(ts, device)
                 marg = P.Marginals(ns, ts)
                 plan = self._sync_plan(P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order,
                                                         lower_order_final, marginals=marg))
@@ -668,8 +676,8 @@ class DPM_Solver:
                         sp.stages = flat[k:k + len(sp.stages)]
                         k += len(sp.stages)
                 all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
-                all_dev = all_times.to(device)
-                outer_dev = timesteps_outer.to(device)
+                all_dev = self._upload(all_times, device)
+                outer_dev = self._upload(timesteps_outer, device)
                 marg = P.Marginals(ns, all_times)
                 alsig = list(zip(marg.alpha.tolist(), marg.sigma.tolist()))
                 tin = self._input_times(all_times, x.shape[0], device)

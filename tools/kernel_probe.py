@@ -77,6 +77,32 @@ def time_form(be, sets, reps=30, warm=5):
     return us[len(us) // 2], us[0]
 
 
+def time_chain(be, form, sdt, n, reps=40, fresh=False):
+    """Emulate the sampling loop's data flow: x_{i+1} = out_i, m1_{i+1} = m_out_i, eps from rotating
+    banks; `fresh` allocates the outputs per step like the solver does (else a fixed ring of 4)."""
+    f = FORMS[form]
+    mk = lambda: torch.randn(n, device="cuda", dtype=sdt)
+    banks = [mk() for _ in range(3)]
+    x, m1, m2 = mk(), mk(), mk()
+    ring = [torch.empty(n, device="cuda", dtype=sdt) for _ in range(8)]
+    ev = []
+    for i in range(reps + 5):
+        a = StepArgs(form=f, n_model=1, predict_x0=True, alpha_e=0.83, sigma_e=0.55, a=0.95, c0=-0.1, c1=0.05,
+                     c2=-0.01, w0=1.02, w1=0.98, w2=0.51, w3=0.5, want_m_out=True, state_dtype=sdt,
+                     x=x, xe=x, e_cond=banks[i % 3], m1=m1, m2=m2 if f == 5 else None)
+        if not fresh:
+            a.out, a.m_out = ring[(2 * i) % 8], ring[(2 * i + 1) % 8]
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        m_new, out = be.step(a)
+        e.record()
+        ev.append((s, e))
+        x, m2, m1 = out, m1, m_new
+    torch.cuda.synchronize()
+    us = sorted(s.elapsed_time(e) * 1e3 for s, e in ev[5:])
+    return us[len(us) // 2], us[0]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--form", default="ms3", choices=sorted(FORMS))
@@ -91,6 +117,7 @@ def main():
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--thr", action="store_true")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--chain", action="store_true")
     ap.add_argument("--peak", type=float, default=6574.5)
     a = ap.parse_args()
     shape = [int(v) for v in a.shape.split(",")]
@@ -98,6 +125,20 @@ def main():
     for v in shape:
         n *= v
     be = ops.CudaBackend()
+    if a.chain:
+        for form in ("diff2", "ms3"):
+            for dt in ("bf16", "f32"):
+                nb = 5 if form == "diff2" else 6
+                b = nb * n * (2 if dt == "bf16" else 4)
+                for variant, threads, ctas in ((0, 0, 0), (1, 256, 2), (1, 128, 4), (1, 512, 1)):
+                    for fresh in (False, True):
+                        be.set_tuning(variant, threads, ctas)
+                        med, mn = time_chain(be, form, DT[dt], n, fresh=fresh)
+                        print(json.dumps(dict(mode="chain", form=form, dtype=dt, variant=variant, threads=threads, ctas=ctas,
+                                              fresh=fresh, median_us=round(med, 1), min_us=round(mn, 1), gbs=round(b / med / 1e3),
+                                              frac=round(b / med / 1e3 / a.peak, 3))), flush=True)
+        be.set_tuning(2, 0, 0)
+        return
     if not a.sweep:
         sdt = DT[a.dtype]
         mdt = DT[a.model_dtype] if a.model_dtype else sdt
