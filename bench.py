@@ -380,6 +380,12 @@ def run_b200(args, w):
     ms = max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = be.launch_count() - launches0
     ksum = be.summary()
+    if os.environ.get("DPM_BENCH_TRACE") and rank == 0:
+        for key, b, a0, a1 in be.records[:2 * w["steps"] + 2]:
+            print(f"trace {key:40s} {a0.elapsed_time(a1) * 1e3:8.1f} us  gap_to_next", file=sys.stderr)
+        recs = be.records
+        for i in range(min(len(recs) - 1, 2 * w["steps"])):
+            print(f"gap {i}: {recs[i][3].elapsed_time(recs[i + 1][2]) * 1e3:7.1f} us", file=sys.stderr)
     value = world * E * n_updates(w) * args.steps / (ms * 1e-3) / 1e9
 
     # ---- e2e: host buffers, H2D of x_T and D2H of the result inside the timed region ----

@@ -263,7 +263,9 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
 
   StageLayout L;
   int threads = 0, stages = 0;
-  // tile = threads * kTmaUnroll packets; default: the largest tile that still leaves >= 3 stages
+  // tile = threads * kTmaUnroll packets. Default 256 threads x 2 CTAs/SM (512 resident threads):
+  // the sweep in profiles/ shows two stages at that size beat more, smaller stages; the tile only
+  // shrinks when two stages of it do not fit.
   const int cand[4] = {t.threads > 0 ? t.threads : 256, 128, 64, 32};
   for (int c = 0; c < (t.threads > 0 ? 1 : 4); ++c) {
     const uint32_t tile_el = (uint32_t)cand[c] * kTmaUnroll * kPacket;
@@ -283,7 +285,7 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
     if (st > kMaxStages) st = kMaxStages;
     threads = cand[c];
     stages = st;
-    if (st >= 3) break;
+    if (st >= 2) break;
   }
   if (stages < 2) return 1;
   const size_t smem = 128 + (size_t)stages * L.bytes;
