@@ -11,6 +11,8 @@
 // (fma(w<0.5 ? w : w-1, hi-lo, w<0.5 ? lo : hi)) and floored with max_val (:423).
 // HBM traffic: one read of the inputs, B floats written.
 #include <cooperative_groups.h>
+#include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch.cuh"
@@ -21,6 +23,9 @@ namespace dpm {
 
 constexpr int kQThreads = 512;
 constexpr int kBins = 2048;
+constexpr int kSamples = 1024;      // sample keys per cluster (fast path)
+constexpr int kLocalCand = 2048;    // bracket keys one CTA may collect
+constexpr int kGlobalCand = 4096;   // bracket keys per cluster (kLocalCand + kGlobalCand = 3*kBins)
 
 struct QParams {
   uint64_t lo;        // floor(pos)
@@ -29,6 +34,8 @@ struct QParams {
   float max_val;
   uint32_t cap;       // key capacity per CTA (elements); 0 => keys are not cached
   uint32_t slice;     // elements of the sample owned by one CTA (multiple of 8 on the packet path)
+  uint32_t fast;      // try the sampled-pivot bracket first
+  int32_t margin;     // half width of the bracket in sample ranks
   float* s_out;
 };
 
@@ -79,23 +86,50 @@ __device__ __forceinline__ Sel select_bin(const uint32_t* tot, uint64_t k, uint3
   return r;
 }
 
+// ---- block-level helpers for the fast path ---------------------------------------------------
+// in-place bitonic sort of n (power of two) uint32 keys in shared memory, ascending
+__device__ __forceinline__ void bitonic_sort(uint32_t* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += kQThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t x = a[i], y = a[l];
+          const bool asc = (i & k) == 0;
+          if ((x > y) == asc) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ctrl word indices (all uint32 in shared memory)
+enum { C_WARP = 0 /*16*/, C_MIN = 32, C_SEL = 40 /*Sel: 4 words*/, C_LO = 48, C_HI = 49, C_LT = 50, C_IN = 51,
+       C_OVF = 52, C_NLOCAL = 53, C_GCOUNT = 54 };
+
 template <typename TE, typename TS, int NE, bool VEC>
 __global__ void __launch_bounds__(kQThreads)
     k_quantile(const __grid_constant__ KParams p, const __grid_constant__ QParams qp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);          // [kBins] local digit histogram
-  uint32_t* total = hist + kBins;                                  // [3][kBins] cluster totals (rank 0)
-  uint32_t* ctrl = total + 3 * kBins;                              // [64] warp sums, min slot, Sel
+  uint32_t* aux = hist + kBins;                                    // [3*kBins]: see below
+  uint32_t* ctrl = aux + 3 * kBins;                                // [64]
   uint32_t* keys = ctrl + 64;                                      // [cap]
-  uint32_t* warp_sums = ctrl;                                      // 16 used
-  uint32_t* min_slot = ctrl + 32;
-  Sel* sel = reinterpret_cast<Sel*>(ctrl + 40);
+  // aux, exact path : total[3][kBins], cluster-wide digit totals (meaningful in CTA 0)
+  // aux, fast path  : lcand[kLocalCand] | gcand[kGlobalCand] (CTA 0; the sample array aliases gcand)
+  uint32_t* total = aux;
+  uint32_t* lcand = aux;
+  uint32_t* gcand = aux + kLocalCand;
+  uint32_t* warp_sums = ctrl + C_WARP;
+  uint32_t* min_slot = ctrl + C_MIN;
+  Sel* sel = reinterpret_cast<Sel*>(ctrl + C_SEL);
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t crank = cluster.block_rank();
   const uint32_t csize = cluster.num_blocks();
   const uint64_t sample = blockIdx.x / csize;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
 
   const uint64_t s_begin = sample * p.per_sample;                  // first element of the sample
   uint64_t c_begin = (uint64_t)crank * qp.slice;                   // slice inside the sample
@@ -104,10 +138,7 @@ __global__ void __launch_bounds__(kQThreads)
   if (c_end > p.per_sample) c_end = p.per_sample;
   const uint32_t cnt = (uint32_t)(c_end - c_begin);
 
-  for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
-  for (int i = tid; i < 3 * kBins; i += kQThreads) total[i] = 0;
-  if (tid == 0) *min_slot = 0xffffffffu;
-  __syncthreads();
+  for (int i = tid; i < 64; i += kQThreads) ctrl[i] = (i == C_MIN) ? 0xffffffffu : 0u;
 
   const TS* __restrict__ gxe = static_cast<const TS*>(p.xe);
   const TE* __restrict__ gec = static_cast<const TE*>(p.ec);
@@ -123,108 +154,229 @@ __global__ void __launch_bounds__(kQThreads)
     return __float_as_uint(fabsf(v));
   };
 
-  // ---- pass A: stream the slice once, stage keys, histogram of bits 31..21 ----
-  if (VEC) {
-    const uint32_t npk = cnt / kPacket;
-    const size_t e0 = s_begin + c_begin;
-    for (uint32_t pk0 = 0; pk0 < npk; pk0 += 2 * kQThreads) {
-      Raw<TS> rx[2];
-      Raw<TE> rc[2], ru[2];
+  // ---- stage the slice: one pass over HBM, keys parked in shared memory ----
+  if (qp.cap) {
+    if (VEC) {
+      const uint32_t npk = cnt / kPacket;
+      const size_t e0 = s_begin + c_begin;
+      for (uint32_t pk0 = 0; pk0 < npk; pk0 += 2 * kQThreads) {
+        Raw<TS> rx[2];
+        Raw<TE> rc[2], ru[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t pk = pk0 + u * kQThreads + tid;
-        if (pk < npk) {
-          const size_t e = e0 + (size_t)pk * kPacket;
-          ldg_pk(rx[u], gxe + e);
-          ldg_pk(rc[u], gec + e);
-          if (NE == 2) ldg_pk(ru[u], geu + e);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t pk = pk0 + u * kQThreads + tid;
-        if (pk < npk) {
-          float fx[8], fc[8], fu[8];
-          unpack(rx[u], fx);
-          unpack(rc[u], fc);
-          if (NE == 2) unpack(ru[u], fu);
-          uint32_t k8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v = model_value<NE>(p, fx[i], fc[i], NE == 2 ? fu[i] : 0.f, 1.f, false);
-            k8[i] = __float_as_uint(fabsf(v));
-            atomicAdd(&hist[k8[i] >> 21], 1u);
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t pk = pk0 + u * kQThreads + tid;
+          if (pk < npk) {
+            const size_t e = e0 + (size_t)pk * kPacket;
+            ldg_pk(rx[u], gxe + e);
+            ldg_pk(rc[u], gec + e);
+            if (NE == 2) ldg_pk(ru[u], geu + e);
           }
-          if (qp.cap) {
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t pk = pk0 + u * kQThreads + tid;
+          if (pk < npk) {
+            float fx[8], fc[8], fu[8], one[8], fT[8];
+            unpack(rx[u], fx);
+            unpack(rc[u], fc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { fu[i] = 0.f; one[i] = 1.f; }
+            if (NE == 2) unpack(ru[u], fu);
+            model_values8<NE>(p, fx, fc, fu, one, false, true, fT);
             uint4* dst = reinterpret_cast<uint4*>(keys + (size_t)pk * kPacket);
-            dst[0] = make_uint4(k8[0], k8[1], k8[2], k8[3]);
-            dst[1] = make_uint4(k8[4], k8[5], k8[6], k8[7]);
+            dst[0] = make_uint4(__float_as_uint(fabsf(fT[0])), __float_as_uint(fabsf(fT[1])),
+                                __float_as_uint(fabsf(fT[2])), __float_as_uint(fabsf(fT[3])));
+            dst[1] = make_uint4(__float_as_uint(fabsf(fT[4])), __float_as_uint(fabsf(fT[5])),
+                                __float_as_uint(fabsf(fT[6])), __float_as_uint(fabsf(fT[7])));
           }
         }
       }
-    }
-  } else {
-    for (uint32_t i = tid; i < cnt; i += kQThreads) {
-      uint32_t k = key_scalar(i);
-      atomicAdd(&hist[k >> 21], 1u);
-      if (qp.cap) keys[i] = k;
+    } else {
+      for (uint32_t i = tid; i < cnt; i += kQThreads) keys[i] = key_scalar(i);
     }
   }
   auto key_at = [&](uint32_t i) -> uint32_t { return qp.cap ? keys[i] : key_scalar(i); };
+  __syncthreads();
 
-  uint32_t* total0 = csize > 1 ? cluster.map_shared_rank(total, 0) : total;
-  uint32_t* min0 = csize > 1 ? cluster.map_shared_rank(min_slot, 0) : min_slot;
+  uint32_t key_lo = 0, key_hi = 0;
+  bool done = false;
 
-  auto merge = [&](int pass, int nb) {
-    __syncthreads();
-    if (pass == 0 && csize > 1) cluster.sync();  // every CTA has zeroed its arrays
-    for (int i = tid; i < nb; i += kQThreads) {
-      uint32_t v = hist[i];
-      if (v) atomicAdd(&total0[pass * kBins + i], v);
+  // =============================== fast path: sampled-pivot bracket ===============================
+  // 1024 evenly strided sample keys -> sort -> two pivots around the target rank -> one counting
+  // pass (no atomics per element) that also compacts the few keys inside the bracket -> CTA 0
+  // finishes with an exact radix select over those candidates. Exact whenever the target ranks fall
+  // inside the bracket (checked with the exact counts); otherwise the full radix select below runs.
+  if (qp.fast) {
+    uint32_t* samp0 = csize > 1 ? cluster.map_shared_rank(gcand, 0) : gcand;
+    const uint32_t per = kSamples / csize;                         // samples contributed by this CTA
+    for (uint32_t j = tid; j < per; j += kQThreads) {
+      const uint32_t idx = cnt ? (uint32_t)(((uint64_t)j * cnt) / per) : 0;
+      samp0[crank * per + j] = cnt ? keys[idx] : 0xffffffffu;
     }
-    if (csize > 1) cluster.sync(); else __syncthreads();
-  };
-
-  merge(0, kBins);
-  Sel sa = select_bin<kBins / kQThreads>(total0, qp.lo, warp_sums, sel);
-
-  // ---- pass B: bits 20..10 among keys whose top digit matches ----
-  for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < cnt; i += kQThreads) {
-    uint32_t k = key_at(i);
-    if ((k >> 21) == sa.bin) atomicAdd(&hist[(k >> 10) & 2047u], 1u);
-  }
-  merge(1, kBins);
-  Sel sb = select_bin<kBins / kQThreads>(total0 + kBins, sa.rank, warp_sums, sel);
-  const uint32_t prefix22 = (sa.bin << 11) | sb.bin;
-
-  // ---- pass C: bits 9..0 ----
-  for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < cnt; i += kQThreads) {
-    uint32_t k = key_at(i);
-    if ((k >> 10) == prefix22) atomicAdd(&hist[k & 1023u], 1u);
-  }
-  merge(2, 1024);
-  Sel sc = select_bin<kBins / kQThreads>(total0 + 2 * kBins, sb.rank, warp_sums, sel);
-  const uint32_t key_lo = (prefix22 << 10) | sc.bin;
-
-  // ---- upper neighbour ----
-  uint32_t key_hi = key_lo;
-  const bool need_next = qp.two && (sc.rank + 1 >= sc.cnt);  // uniform across the cluster
-  if (need_next) {
-    uint32_t m = 0xffffffffu;
-    for (uint32_t i = tid; i < cnt; i += kQThreads) {
-      uint32_t k = key_at(i);
-      if (k > key_lo && k < m) m = k;
+    if (csize > 1) cluster.sync(); else __syncthreads();           // (1) samples in CTA 0
+    if (crank == 0) {
+      bitonic_sort(gcand, kSamples);
+      if (tid == 0) {
+        const int64_t ps = (int64_t)(((unsigned __int128)qp.lo * kSamples) / p.per_sample);
+        const int64_t lo_i = ps - qp.margin, hi_i = ps + qp.margin + 1;
+        const uint32_t lo_k = lo_i < 0 ? 0u : gcand[lo_i];
+        const uint32_t hi_k = hi_i >= kSamples ? 0xffffffffu : gcand[hi_i];
+        for (uint32_t r = 0; r < csize; ++r) {
+          uint32_t* c = csize > 1 ? cluster.map_shared_rank(ctrl, r) : ctrl;
+          c[C_LO] = lo_k;
+          c[C_HI] = hi_k;
+        }
+      }
+    }
+    if (csize > 1) cluster.sync(); else __syncthreads();           // (2) pivots everywhere
+    const uint32_t lo_k = ctrl[C_LO], hi_k = ctrl[C_HI];
+    uint32_t c_lt = 0;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kQThreads) {
+      const uint32_t i = i0 + tid;
+      const uint32_t k = i < cnt ? keys[i] : 0xffffffffu;
+      const bool in = i < cnt && k >= lo_k && k <= hi_k;
+      c_lt += (i < cnt && k < lo_k) ? 1u : 0u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, in);
+      if (bal) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctrl[C_NLOCAL], (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (in && pos < kLocalCand) lcand[pos] = k;
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0 && m != 0xffffffffu) atomicMin(min0, m);
-    if (csize > 1) cluster.sync(); else __syncthreads();
-    key_hi = *min0;
+    for (int o = 16; o > 0; o >>= 1) c_lt += __shfl_xor_sync(0xffffffffu, c_lt, o);
+    if (lane == 0 && c_lt) atomicAdd(&ctrl[C_LT + 8], c_lt);       // local scratch word (ctrl[58])
+    __syncthreads();
+    const uint32_t n_local = ctrl[C_NLOCAL];
+    const uint32_t my_lt = ctrl[C_LT + 8];
+    // publish counts to every CTA, reserve a range in CTA 0's candidate list, copy the local list
+    uint32_t* ctrl0 = csize > 1 ? cluster.map_shared_rank(ctrl, 0) : ctrl;
+    uint32_t* gc0 = csize > 1 ? cluster.map_shared_rank(gcand, 0) : gcand;
+    if (tid == 0) {
+      const uint32_t base = atomicAdd(&ctrl0[C_GCOUNT], n_local);
+      ctrl[C_SEL + 4] = base;                                      // ctrl[44]
+      const uint32_t ovf = (n_local > kLocalCand || base + n_local > kGlobalCand) ? 1u : 0u;
+      for (uint32_t r = 0; r < csize; ++r) {
+        uint32_t* c = csize > 1 ? cluster.map_shared_rank(ctrl, r) : ctrl;
+        atomicAdd(&c[C_LT], my_lt);
+        atomicAdd(&c[C_IN], n_local);
+        if (ovf) atomicOr(&c[C_OVF], 1u);
+      }
+    }
+    __syncthreads();
+    {
+      const uint32_t base = ctrl[C_SEL + 4];
+      if (n_local <= kLocalCand && base + n_local <= kGlobalCand) {
+        if (crank == 0 && csize == 1) {
+          // single CTA: lcand and gcand are distinct regions of the same aux array
+        }
+        for (uint32_t i = tid; i < n_local; i += kQThreads) gc0[base + i] = lcand[i];
+      }
+    }
+    if (csize > 1) cluster.sync(); else __syncthreads();           // (3) counts + candidates in CTA 0
+    const uint64_t C_lt = ctrl[C_LT], C_in = ctrl[C_IN];
+    const bool ok = !ctrl[C_OVF] && qp.lo >= C_lt && (qp.lo + qp.two) < C_lt + C_in;
+    if (ok) {
+      if (crank != 0) return;                                      // CTA 0 owns everything it still needs
+      const uint32_t m = (uint32_t)C_in;
+      uint64_t rank = qp.lo - C_lt;
+      // exact 11/11/10-bit radix select over the candidates (block-local)
+      uint32_t prefix = 0;
+      Sel sc;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += kQThreads) {
+          const uint32_t k = gcand[i];
+          if (pass == 0) atomicAdd(&hist[k >> 21], 1u);
+          else if (pass == 1) { if ((k >> 21) == prefix) atomicAdd(&hist[(k >> 10) & 2047u], 1u); }
+          else { if ((k >> 10) == prefix) atomicAdd(&hist[k & 1023u], 1u); }
+        }
+        __syncthreads();
+        sc = select_bin<kBins / kQThreads>(hist, rank, warp_sums, sel);
+        rank = sc.rank;
+        prefix = pass == 0 ? sc.bin : (pass == 1 ? ((prefix << 11) | sc.bin) : ((prefix << 10) | sc.bin));
+      }
+      key_lo = prefix;
+      key_hi = key_lo;
+      if (qp.two && (sc.rank + 1 >= sc.cnt)) {
+        uint32_t mn = 0xffffffffu;
+        for (uint32_t i = tid; i < m; i += kQThreads) {
+          const uint32_t k = gcand[i];
+          if (k > key_lo && k < mn) mn = k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0 && mn != 0xffffffffu) atomicMin(min_slot, mn);
+        __syncthreads();
+        key_hi = *min_slot;
+      }
+      done = true;
+    }
   }
+
+  // =============================== exact path: full radix select ===================================
+  if (!done) {
+    for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
+    for (int i = tid; i < 3 * kBins; i += kQThreads) total[i] = 0;
+    if (tid == 0) *min_slot = 0xffffffffu;
+    __syncthreads();
+    uint32_t* total0 = csize > 1 ? cluster.map_shared_rank(total, 0) : total;
+    uint32_t* min0 = csize > 1 ? cluster.map_shared_rank(min_slot, 0) : min_slot;
+    if (csize > 1) cluster.sync();                                 // every CTA has zeroed its arrays
+
+    auto merge = [&](int pass, int nb) {
+      __syncthreads();
+      for (int i = tid; i < nb; i += kQThreads) {
+        uint32_t v = hist[i];
+        if (v) atomicAdd(&total0[pass * kBins + i], v);
+      }
+      if (csize > 1) cluster.sync(); else __syncthreads();
+    };
+
+    for (uint32_t i = tid; i < cnt; i += kQThreads) atomicAdd(&hist[key_at(i) >> 21], 1u);
+    merge(0, kBins);
+    Sel sa = select_bin<kBins / kQThreads>(total0, qp.lo, warp_sums, sel);
+
+    for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += kQThreads) {
+      uint32_t k = key_at(i);
+      if ((k >> 21) == sa.bin) atomicAdd(&hist[(k >> 10) & 2047u], 1u);
+    }
+    merge(1, kBins);
+    Sel sb = select_bin<kBins / kQThreads>(total0 + kBins, sa.rank, warp_sums, sel);
+    const uint32_t prefix22 = (sa.bin << 11) | sb.bin;
+
+    for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += kQThreads) {
+      uint32_t k = key_at(i);
+      if ((k >> 10) == prefix22) atomicAdd(&hist[k & 1023u], 1u);
+    }
+    merge(2, 1024);
+    Sel sc = select_bin<kBins / kQThreads>(total0 + 2 * kBins, sb.rank, warp_sums, sel);
+    key_lo = (prefix22 << 10) | sc.bin;
+    key_hi = key_lo;
+    const bool need_next = qp.two && (sc.rank + 1 >= sc.cnt);      // uniform across the cluster
+    if (need_next) {
+      uint32_t m = 0xffffffffu;
+      for (uint32_t i = tid; i < cnt; i += kQThreads) {
+        uint32_t k = key_at(i);
+        if (k > key_lo && k < m) m = k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0 && m != 0xffffffffu) atomicMin(min0, m);
+      if (csize > 1) cluster.sync(); else __syncthreads();
+      key_hi = *min0;
+    }
+    if (csize > 1) cluster.sync();  // keep CTA 0's shared memory alive until every peer has read it
+  }
+
   if (crank == 0 && tid == 0) {
     const float a = __uint_as_float(key_lo), b = __uint_as_float(key_hi);
     const float d = b - a;
@@ -233,7 +385,6 @@ __global__ void __launch_bounds__(kQThreads)
     s = fmaxf(s, qp.max_val);  // torch.maximum(s, max_val) :423
     qp.s_out[sample] = s;
   }
-  if (csize > 1) cluster.sync();  // keep CTA 0's shared memory alive until every peer has read it
 }
 
 typedef void (*QKernel)(const KParams, const QParams);
@@ -291,6 +442,13 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
   if (cap == 0) { cs = 8; slice = slice_for(cs); }
   qp.cap = cap;
   qp.slice = (uint32_t)slice;
+  // sampled-pivot bracket: 4 sigma of the sample-rank of the target quantile, plus slack
+  {
+    const double f = ps > 1 ? (double)qp.lo / (double)(ps - 1) : 0.0;
+    qp.margin = (int32_t)(4.0 * sqrt((double)kSamples * f * (1.0 - f)) + 3.0);
+    qp.fast = (cap != 0 && ps >= 8192 && cs <= 16) ? 1u : 0u;
+    if (const char* e = getenv("DPM_QUANTILE_EXACT_ONLY")) qp.fast = (e[0] == '1') ? 0u : qp.fast;
+  }
   if (slice > 0xffffffffull) { set_error("per_sample too large"); return DPM_ERR_UNSUPPORTED; }
 
   const size_t smem = fixed + (size_t)cap * sizeof(uint32_t);

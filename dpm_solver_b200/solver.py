@@ -208,11 +208,23 @@ class DPM_Solver:
         self.state_dtype = state_dtype
         self.plan_broadcast = bool(plan_broadcast)
 
-    def _sync_plan(self, coeffs):
+    def _sync_plan(self, coeffs, key=None):
+        """Rank 0's coefficients on every rank. One broadcast per sampling configuration: the synced
+        plan is cached under the plan key, so steady-state sample() calls issue no collective."""
         if not self.plan_broadcast:
             return coeffs
         from .distributed import broadcast_plan
-        return broadcast_plan(coeffs)
+        if key is None:
+            return broadcast_plan(coeffs)
+        cache = self.__dict__.setdefault("_synced_cache", {})
+        k = (self._schedule_key(), self.algorithm_type) + key
+        hit = cache.get(k)
+        if hit is None:
+            hit = broadcast_plan(coeffs)
+            if len(cache) >= self._CACHE_MAX:
+                cache.pop(next(iter(cache)))
+            cache[k] = hit
+        return hit
 
     # -- small helpers ------------------------------------------------------------------------
     @property
@@ -243,6 +255,42 @@ class DPM_Solver:
         if isinstance(w, WrappedModel) and w.fusable:
             return w.raw(x, t_dev.expand((x.shape[0])), t_input)
         return RawOutput(self.model(x, t_dev), None, PARAM_NOISE, 1.0)
+
+    _CACHE_MAX = 16
+
+    def _schedule_key(self):
+        ns = self.noise_schedule
+        if getattr(ns, "schedule", None) == "discrete":
+            return ("discrete", id(ns.log_alpha_array), id(ns.t_array), ns.total_N)
+        return (getattr(ns, "schedule", None), getattr(ns, "beta_0", None), getattr(ns, "beta_1", None), id(ns))
+
+    def _host_plan(self, key, build):
+        """Coefficient plan of a run, cached per (schedule, algorithm, sampling arguments): repeated
+        sample() calls with the same configuration (serving) skip the host scalar work entirely."""
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        k = (self._schedule_key(), self.algorithm_type) + key
+        hit = cache.get(k)
+        if hit is None:
+            hit = build()
+            if len(cache) >= self._CACHE_MAX:
+                cache.pop(next(iter(cache)))
+            cache[k] = hit
+        return hit
+
+    def _device_tables(self, key, t_host, batch, device, n_eval=None):
+        """Device copies of the time grid and of the model-input time matrix, cached with the plan
+        (they depend on the batch size and the device only)."""
+        cache = self.__dict__.setdefault("_table_cache", {})
+        k = (self._schedule_key(), self.algorithm_type) + key + (batch, str(device), id(self._wrapped))
+        hit = cache.get(k)
+        if hit is None:
+            t_dev = self._upload(t_host, device)
+            tin = self._input_times(t_host if n_eval is None else t_host[:n_eval], batch, device)
+            hit = (t_dev, tin)
+            if len(cache) >= self._CACHE_MAX:
+                cache.pop(next(iter(cache)))
+            cache[k] = hit
+        return hit
 
     @staticmethod
     def _upload(t_host: torch.Tensor, device):
@@ -610,16 +658,22 @@ class DPM_Solver:
                     raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
                 if order not in (1, 2, 3):
                     raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
-                ts = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device='cpu')
-                assert ts.shape[0] - 1 == steps
-                ts_dev = self._upload(ts, device)
-                marg = P.Marginals(ns, ts)
-                plan = self._sync_plan(P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order,
-                                                        lower_order_final, marginals=marg))
+                key = ("multistep", steps, order, skip_type, t_T, t_0, solver_type, lower_order_final)
+
+                def build():
+                    ts = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device='cpu')
+                    assert ts.shape[0] - 1 == steps
+                    marg = P.Marginals(ns, ts)
+                    plan = P.multistep_plan(ns, self.algorithm_type, solver_type, ts, order, lower_order_final,
+                                            marginals=marg)
+                    # (alpha_t, sigma_t) per grid point: scalars of the eps->x0 / parameterisation step
+                    return ts, plan, list(zip(marg.alpha.tolist(), marg.sigma.tolist()))
+
+                ts, plan, alsig = self._host_plan(key, build)
+                plan = self._sync_plan(plan, key)
+                ts_dev, tin = self._device_tables(key, ts, x.shape[0], device)
                 # model evaluation 0, then one fused launch per step:
                 #   m_{i} = convert(net(x_i, t_i));  x_{i+1} = update(x_i, m_i, m_{i-1}, m_{i-2})
-                alsig = list(zip(marg.alpha.tolist(), marg.sigma.tolist()))   # (alpha_t, sigma_t) per grid point
-                tin = self._input_times(ts, x.shape[0], device)
                 step = 0
                 raw = self._evaluate(x, ts_dev[0], None if tin is None else tin[0])
                 xe = x
@@ -650,37 +704,45 @@ class DPM_Solver:
                         raw = self._evaluate(x, t, None if tin is None else tin[step])
                         xe = x
             elif method in ['singlestep', 'singlestep_fixed']:
-                if method == 'singlestep':
-                    timesteps_outer, orders = self.get_orders_and_timesteps_for_singlestep_solver(
-                        steps=steps, order=order, skip_type=skip_type, t_T=t_T, t_0=t_0, device='cpu')
-                else:
-                    K = steps // order
-                    orders = [order, ] * K
-                    timesteps_outer = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=K, device='cpu')
-                if solver_type not in ['dpmsolver', 'taylor'] and max(orders) >= 2:
-                    raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
-                # host plan for the whole run, model-evaluation times uploaded once
-                plans = []
-                for step, o in enumerate(orders):
-                    s, t = timesteps_outer[step], timesteps_outer[step + 1]
-                    timesteps_inner = self.get_time_steps(skip_type=skip_type, t_T=s.item(), t_0=t.item(), N=o, device='cpu')
-                    lambda_inner = ns.marginal_lambda(timesteps_inner)
-                    h = lambda_inner[-1] - lambda_inner[0]
-                    r1 = None if o <= 1 else (lambda_inner[1] - lambda_inner[0]) / h
-                    r2 = None if o <= 2 else (lambda_inner[2] - lambda_inner[0]) / h
-                    plans.append(P.singlestep_plan(ns, self.algorithm_type, solver_type, o, s, t, r1, r2))
+                key = (method, steps, order, skip_type, t_T, t_0, solver_type)
+
+                def build():
+                    if method == 'singlestep':
+                        timesteps_outer, orders = self.get_orders_and_timesteps_for_singlestep_solver(
+                            steps=steps, order=order, skip_type=skip_type, t_T=t_T, t_0=t_0, device='cpu')
+                    else:
+                        K = steps // order
+                        orders = [order, ] * K
+                        timesteps_outer = self.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=K, device='cpu')
+                    if solver_type not in ['dpmsolver', 'taylor'] and max(orders) >= 2:
+                        raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+                    # host plan for the whole run (:1221-1228 evaluated up front, no .item() syncs later)
+                    plans = []
+                    for i, o in enumerate(orders):
+                        s_, t_ = timesteps_outer[i], timesteps_outer[i + 1]
+                        timesteps_inner = self.get_time_steps(skip_type=skip_type, t_T=s_.item(), t_0=t_.item(), N=o, device='cpu')
+                        lambda_inner = ns.marginal_lambda(timesteps_inner)
+                        h = lambda_inner[-1] - lambda_inner[0]
+                        r1 = None if o <= 1 else (lambda_inner[1] - lambda_inner[0]) / h
+                        r2 = None if o <= 2 else (lambda_inner[2] - lambda_inner[0]) / h
+                        plans.append(P.singlestep_plan(ns, self.algorithm_type, solver_type, o, s_, t_, r1, r2))
+                    all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
+                    marg = P.Marginals(ns, all_times)
+                    return (torch.cat([all_times, timesteps_outer.reshape(-1)]), plans,
+                            list(zip(marg.alpha.tolist(), marg.sigma.tolist())))
+
+                packed, plans, alsig = self._host_plan(key, build)
                 if self.plan_broadcast:
-                    flat = self._sync_plan([co for sp in plans for co in sp.stages])
+                    flat = self._sync_plan([co for sp in plans for co in sp.stages], key)
+                    plans = [P.SinglestepPlan(sp.order, sp.times, []) for sp in plans]
                     k = 0
                     for sp in plans:
-                        sp.stages = flat[k:k + len(sp.stages)]
-                        k += len(sp.stages)
-                all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
-                all_dev = self._upload(all_times, device)
-                outer_dev = self._upload(timesteps_outer, device)
-                marg = P.Marginals(ns, all_times)
-                alsig = list(zip(marg.alpha.tolist(), marg.sigma.tolist()))
-                tin = self._input_times(all_times, x.shape[0], device)
+                        n_st = {1: 1, 2: 2, 3: 3}[sp.order]
+                        sp.stages = flat[k:k + n_st]
+                        k += n_st
+                n_eval = len(alsig)
+                packed_dev, tin = self._device_tables(key, packed, x.shape[0], device, n_eval)
+                all_dev, outer_dev = packed_dev[:n_eval], packed_dev[n_eval:]
                 k = 0
                 step = 0
                 for step, sp in enumerate(plans):

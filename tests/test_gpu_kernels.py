@@ -187,15 +187,16 @@ def test_dynamic_threshold_exact(cuda_backend, per_sample, B, sdt, mdt, nm):
 def test_dynamic_threshold_ties_and_constants(cuda_backend):
     """Heavy ties (quantised values, all-equal samples, zeros) select the same order statistics."""
     from oracle import dpm_oracle as O
-    per_sample, B = 4096, 6
-    x = (torch.randn(B, per_sample, generator=torch.Generator().manual_seed(1)) * 4).round() / 4
-    x[1] = 0.75
-    x[2] = 0.0
-    a = StepArgs(form=FORM_NONE, n_model=1, e_cond=torch.zeros(B * per_sample), xe=x.reshape(-1), predict_x0=True,
-                 alpha_e=1.0, sigma_e=0.0, per_sample=per_sample, state_dtype=torch.float32)
-    for q in (0.995, 0.25, 0.9999):
-        got = cuda_backend.dynamic_threshold(to_dev(a), q, 0.0).cpu().numpy()
-        np.testing.assert_array_equal(got, O.quantile_abs(x.numpy(), q))
+    for per_sample, B in ((4096, 6), (16384, 6), (3 * 128 * 128, 5)):   # exact path / bracket path (1 CTA, cluster)
+        x = (torch.randn(B, per_sample, generator=torch.Generator().manual_seed(1)) * 4).round() / 4
+        x[1] = 0.75
+        x[2] = 0.0
+        x[3, : per_sample // 2] = 9.5      # half the sample tied at the top
+        a = StepArgs(form=FORM_NONE, n_model=1, e_cond=torch.zeros(B * per_sample), xe=x.reshape(-1), predict_x0=True,
+                     alpha_e=1.0, sigma_e=0.0, per_sample=per_sample, state_dtype=torch.float32)
+        for q in (0.995, 0.25, 0.9999, 0.75):
+            got = cuda_backend.dynamic_threshold(to_dev(a), q, 0.0).cpu().numpy()
+            np.testing.assert_array_equal(got, O.quantile_abs(x.numpy(), q))
 
 
 def test_quantile_golden(golden, cuda_backend):
