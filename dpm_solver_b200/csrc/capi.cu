@@ -332,8 +332,12 @@ int dpm_data_prediction(void* x0, const void* x, const void* eps, float alpha_t,
   return dpm_step(&d, stream);
 }
 
+size_t dpm_dynamic_threshold_workspace(uint64_t n_samples, uint64_t per_sample) {
+  return quantile_workspace_bytes(n_samples, per_sample);
+}
+
 int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, float max_val,
-                          dpm_stream_t stream) {
+                          void* workspace, size_t workspace_bytes, dpm_stream_t stream) {
   if (s_out == nullptr) { set_error("s_out is NULL"); return DPM_ERR_ARG; }
   if (!(q >= 0.f && q <= 1.f)) { set_error("q must be in [0,1]"); return DPM_ERR_ARG; }
   KParams p;
@@ -341,7 +345,8 @@ int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, floa
   int rc = build_params(desc, &p, &nd, true);
   if (rc != DPM_OK) return rc;
   if (p.n == 0) return DPM_OK;
-  rc = launch_quantile(s_out, p, p.n / p.per_sample, q, max_val, static_cast<cudaStream_t>(stream));
+  rc = launch_quantile(s_out, p, p.n / p.per_sample, q, max_val, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
   if (rc != DPM_OK) return rc;
   return finish(static_cast<cudaStream_t>(stream));
 }

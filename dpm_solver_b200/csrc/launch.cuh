@@ -26,6 +26,7 @@ int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream);
 int launch_step_scalar(const KParams& p, cudaStream_t stream);
 int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream);
 int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q, float max_val,
-                    cudaStream_t stream);
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t quantile_workspace_bytes(uint64_t n_samples, uint64_t per_sample);
 
 }  // namespace dpm

@@ -177,9 +177,13 @@ class CudaBackend:
         d, keep, ref, _ = self._fill(a)
         if a.per_sample <= 0 or ref.numel() % a.per_sample:
             raise ValueError("dpm_solver_b200: per_sample must divide numel")
-        s = torch.empty(ref.numel() // a.per_sample, dtype=torch.float32, device=ref.device)
+        nb = ref.numel() // a.per_sample
+        s = torch.empty(nb, dtype=torch.float32, device=ref.device)
+        ws_bytes = int(self._lib.dpm_dynamic_threshold_workspace(nb, a.per_sample))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device) if ws_bytes else None
         self._launch(ref.device, self._lib.dpm_dynamic_threshold, C.c_void_p(s.data_ptr()), C.byref(d),
-                     C.c_float(q), C.c_float(max_val))
+                     C.c_float(q), C.c_float(max_val), C.c_void_p(ws.data_ptr() if ws is not None else None),
+                     C.c_size_t(ws_bytes))
         return s
 
     def launch_count(self) -> int:

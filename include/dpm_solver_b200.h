@@ -192,11 +192,15 @@ DPM_API int dpm_data_prediction(void* x0, const void* x, const void* eps, float 
  * s_b = max(quantile(|x0_b|, q), max_val) with torch.quantile's linear interpolation between
  * the two adjacent order statistics (rank arithmetic in fp32). x0 is recomputed on the fly from
  * the same inputs dpm_step() takes (desc->x/xe, e_cond, e_uncond, param, guidance, alpha_e,
- * sigma_e, predict_x0 must be 1); desc->thr/form/out/m* are ignored. Exact (radix select on
- * the fp32 bit pattern, one thread-block cluster per sample, keys staged in shared memory).
- * s_out: fp32 [n/per_sample]. */
+ * sigma_e; predict_x0 must be 1); desc->thr/form/out/m* are ignored. Always exact.
+ * With a workspace of dpm_dynamic_threshold_workspace() bytes (16-byte aligned device memory,
+ * contents irrelevant) samples of >= 8192 elements take the streaming pipeline: pivot sampling,
+ * one HBM-rate count/compact pass, exact finish on the ~2 % of keys inside the bracket. Without
+ * it (workspace == NULL), or for smaller samples, one thread-block cluster per sample runs a
+ * radix select with the keys staged in (distributed) shared memory. s_out: fp32 [n/per_sample]. */
+DPM_API size_t dpm_dynamic_threshold_workspace(uint64_t n_samples, uint64_t per_sample);
 DPM_API int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, float max_val,
-                          dpm_stream_t stream);
+                                  void* workspace, size_t workspace_bytes, dpm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -177,11 +177,17 @@ def test_dynamic_threshold_exact(cuda_backend, per_sample, B, sdt, mdt, nm):
     n = per_sample * B
     a = make_args(FORM_NONE, nm, n, sdt, mdt, predict_x0=True, seed=per_sample % 97)
     a.per_sample = per_sample
-    for q, max_val in ((0.995, 1.0), (0.5, 0.1), (1.0, 0.0), (0.0, 0.0)):
-        got = cuda_backend.dynamic_threshold(to_dev(a), q, max_val).cpu().numpy()
-        x0 = OracleBackend()._model_value(a, None).reshape(B, -1)
+    import os
+    x0 = OracleBackend()._model_value(a, None).reshape(B, -1)
+    for q, max_val in ((0.995, 1.0), (0.5, 0.1), (1.0, 0.0), (0.0, 0.0), (0.97, 0.0)):
         ref = np.maximum(O.quantile_abs(x0, q), np.float32(max_val))
-        np.testing.assert_array_equal(got, ref)
+        for impl in ("pipeline", "cluster"):     # streaming pipeline (default) and the cluster radix kernel
+            os.environ["DPM_QUANTILE_IMPL"] = impl
+            try:
+                got = cuda_backend.dynamic_threshold(to_dev(a), q, max_val).cpu().numpy()
+            finally:
+                os.environ.pop("DPM_QUANTILE_IMPL", None)
+            np.testing.assert_array_equal(got, ref, err_msg=f"{impl} q={q}")
 
 
 def test_dynamic_threshold_ties_and_constants(cuda_backend):
