@@ -24,7 +24,7 @@ class StepDesc(C.Structure):
     """struct dpm_step_desc"""
     _fields_ = [
         ("x", C.c_void_p), ("xe", C.c_void_p), ("m0", C.c_void_p), ("m1", C.c_void_p),
-        ("m2", C.c_void_p), ("m_out", C.c_void_p), ("out", C.c_void_p),
+        ("m2", C.c_void_p), ("m_out", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p),
         ("e_cond", C.c_void_p), ("e_uncond", C.c_void_p), ("thr", C.c_void_p),
         ("n", C.c_uint64), ("per_sample", C.c_uint64),
         ("state_dtype", C.c_int32), ("model_dtype", C.c_int32), ("form", C.c_int32),

@@ -132,6 +132,7 @@ static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for
   kp->ec = d->e_cond; kp->eu = d->e_uncond;
   kp->m_out = for_quantile ? nullptr : d->m_out;
   kp->out = for_quantile ? nullptr : d->out;
+  kp->out2 = (for_quantile || form == DPM_FORM_NONE) ? nullptr : d->out2;
   kp->thr = for_quantile ? nullptr : d->thr;
   kp->n = d->n;
   kp->npk = (uint32_t)(d->n / kPacket);
@@ -172,6 +173,7 @@ static bool all_aligned(const KParams& p, const Needs& nd) {
   if (nd.eu) ok &= aligned(p.eu, md);
   if (p.m_out) ok &= aligned(p.m_out, sd);
   if (p.out) ok &= aligned(p.out, sd);
+  if (p.out2) ok &= aligned(p.out2, sd);
   return ok;
 }
 
@@ -181,7 +183,7 @@ static KParams shifted(const KParams& p, uint64_t elems) {
   t.x = off(p.x, sd, elems); t.xe = off(p.xe, sd, elems); t.m0 = off(p.m0, sd, elems);
   t.m1 = off(p.m1, sd, elems); t.m2 = off(p.m2, sd, elems);
   t.ec = off(p.ec, md, elems); t.eu = off(p.eu, md, elems);
-  t.m_out = off(p.m_out, sd, elems); t.out = off(p.out, sd, elems);
+  t.m_out = off(p.m_out, sd, elems); t.out = off(p.out, sd, elems); t.out2 = off(p.out2, sd, elems);
   t.n = p.n - elems;
   t.elem_offset = elems;
   return t;

@@ -28,6 +28,7 @@ struct KParams {
   const void* eu;
   void* m_out;
   void* out;
+  void* out2;
   const float* thr;
   uint64_t n;           // elements (scalar kernel) / unused by packet kernels
   uint32_t npk;         // number of full packets

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(kMaxThreads)
   const TE* __restrict__ geu = static_cast<const TE*>(p.eu);
   TS* __restrict__ gmo = static_cast<TS*>(p.m_out);
   TS* __restrict__ go = static_cast<TS*>(p.out);
+  TS* __restrict__ go2 = static_cast<TS*>(p.out2);
 
   const uint32_t npk = p.npk;
   const uint32_t tile_pk = blockDim.x * kUnroll;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(kMaxThreads)
           Raw<TS> ro;
           pack(ro, fo);
           stg_pk(go + e, ro);
+          if (go2 != nullptr) stg_pk(go2 + e, ro);
         }
       }
     }
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KPa
       default: continue;
     }
     store_any(p.out, sd, i, o);
+    if (p.out2) store_any(p.out2, sd, i, o);
   }
 }
 

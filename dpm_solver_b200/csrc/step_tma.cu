@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
     if (tid == 0) {
       const uint32_t bs = el * Traits<TS>::kBytes;
       if (has_mo) bulk_s2g(static_cast<char*>(p.m_out) + e0 * Traits<TS>::kBytes, st + L.mo, bs);
-      if (FORM != DPM_FORM_NONE) bulk_s2g(static_cast<char*>(p.out) + e0 * Traits<TS>::kBytes, st + L.o, bs);
+      if (FORM != DPM_FORM_NONE) {
+        bulk_s2g(static_cast<char*>(p.out) + e0 * Traits<TS>::kBytes, st + L.o, bs);
+        if (p.out2 != nullptr) bulk_s2g(static_cast<char*>(p.out2) + e0 * Traits<TS>::kBytes, st + L.o, bs);
+      }
       bulk_commit();
       const uint64_t next = tile + (uint64_t)stages * gridDim.x;
       if (next < ntiles) issue_loads((uint32_t)next, s);
@@ -251,12 +254,15 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const bool need_x = p.form != DPM_FORM_NONE;
   TmaKernel k = pick_tma(p.model_dtype, p.state_dtype, p.n_model, p.form);
   if (k == nullptr) return 1;
-  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : 2;
   const uint32_t ss = p.state_dtype == DPM_F32 ? 4 : 2, ms = p.model_dtype == DPM_F32 ? 4 : 2;
   const bool sep_xe = p.n_model > 0 && p.use_xe && need_x && !p.xe_is_x;
   const bool m1 = p.form == DPM_FORM_LIN2 || p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_DIFF2 ||
                   p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
   const bool m2 = p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
+  const int n_streams = (need_x || (p.n_model > 0 && p.use_xe)) + sep_xe + p.n_model + (p.n_model == 0) + m1 + m2 +
+                        (p.n_model > 0 && p.m_out != nullptr) + need_x;
+  // 16-bit sweep (profiles/): <= 4 streams run best with 3 CTAs/SM (768 resident threads), more with 2
+  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : ((n_streams <= 4 && ss == 2) ? 3 : 2);
   // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
   const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
   const size_t budget = per_cta < (size_t)max_smem_optin() ? per_cta : (size_t)max_smem_optin();

@@ -53,6 +53,7 @@ class StepArgs:
     want_m_out: bool = False          # materialise the computed model value (n_model >= 1)
     state_dtype: Optional[torch.dtype] = None  # dtype of x/xe/m*/outputs; default: from tensors
     out: Optional[torch.Tensor] = None     # optional preallocated outputs
+    out2: Optional[torch.Tensor] = None    # optional second copy of x_t (doubled CFG batch)
     m_out: Optional[torch.Tensor] = None
 
     def state_tensors(self):
@@ -158,6 +159,11 @@ class CudaBackend:
             if not out.is_contiguous():
                 raise ValueError("dpm_solver_b200: preallocated out must be contiguous")
             d.out = out.data_ptr()
+            if a.out2 is not None:
+                self._check(a.out2, "out2", ref.device, ref.numel(), sdt)
+                if not a.out2.is_contiguous():
+                    raise ValueError("dpm_solver_b200: out2 must be contiguous")
+                d.out2 = a.out2.data_ptr()
         self._launch(ref.device, self._lib.dpm_step, C.byref(d))
         return m_out, out
 

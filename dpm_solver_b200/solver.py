@@ -99,7 +99,7 @@ class WrappedModel:
             self._c_in = (key, torch.cat([self.unconditional_condition, self.condition]))
         return self._c_in[1]
 
-    def raw(self, x, t_continuous, t_input=None) -> RawOutput:
+    def raw(self, x, t_continuous, t_input=None, x_in=None) -> RawOutput:
         """Run the network exactly as the reference does, return its un-combined output(s).
 
         `t_input`, when given, is the precomputed model-input time vector (`input_rows(B)` long,
@@ -110,7 +110,8 @@ class WrappedModel:
         if self.guidance_type == "classifier-free":
             if not self.uses_cfg:
                 return RawOutput(self._call_model(x, t_continuous, cond=self.condition, t_input=t_input), None, param, 1.0)
-            x_in = torch.cat([x] * 2)
+            if x_in is None:
+                x_in = torch.cat([x] * 2)                      # :326 (the solver hands over a prebuilt one)
             t_in = None if t_input is not None else torch.cat([t_continuous] * 2)
             out_u, out_c = self._call_model(x_in, t_in, cond=self._cond_in(), t_input=t_input).chunk(2)  # uncond first
             return RawOutput(out_c, out_u, param, float(self.guidance_scale))
@@ -253,8 +254,20 @@ class DPM_Solver:
         """Call the user's network at (x, t); same call the reference makes through self.model."""
         w = self._wrapped
         if isinstance(w, WrappedModel) and w.fusable:
-            return w.raw(x, t_dev.expand((x.shape[0])), t_input)
+            pair = self.__dict__.get("_xin_pair")
+            x_in = pair[1] if (pair is not None and pair[0] is x) else None
+            return w.raw(x, t_dev.expand((x.shape[0])), t_input, x_in)
         return RawOutput(self.model(x, t_dev), None, PARAM_NOISE, 1.0)
+
+    def _dup_target(self, x):
+        """Under CFG the network consumes cat([x]*2) (:326). When nothing can touch x between the
+        update and the next evaluation, the update kernel writes x_t straight into both halves of a
+        [2B, ...] buffer: returns (x_in, first half, second half) or None."""
+        w = self._wrapped
+        if self.correcting_xt_fn is not None or not (isinstance(w, WrappedModel) and w.fusable and w.uses_cfg):
+            return None
+        x_in = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        return x_in, x_in[:x.shape[0]], x_in[x.shape[0]:]
 
     _CACHE_MAX = 16
 
@@ -325,7 +338,7 @@ class DPM_Solver:
                 or raw.e_cond.dtype != sdtype)
 
     def _post_model(self, raw: RawOutput, xe, t_dev, alsig, co: Optional[P.Coeffs] = None, x=None,
-                    m1=None, m2=None, want_m: bool = True):
+                    m1=None, m2=None, want_m: bool = True, dup_out: bool = False):
         """The fused post-model step: buffered value from `raw` (+ optional update `co`).
 
         Returns (m_new, x_next). Falls back to two launches only when a user-supplied
@@ -351,7 +364,13 @@ class DPM_Solver:
             return m_new, x_next
         self._fill_update(a, co, x, m1, m2)
         a.want_m_out = want_m
-        return be.step(a)
+        dup = self._dup_target(x) if dup_out else None
+        if dup is not None:
+            a.out, a.out2 = dup[1], dup[2]
+        m_new, x_next = be.step(a)
+        if dup is not None:
+            self._xin_pair = (x_next, dup[0])
+        return m_new, x_next
 
     @staticmethod
     def _state_like(t, sd):
@@ -481,7 +500,8 @@ class DPM_Solver:
         return x_t
 
     def _run_singlestep(self, x, sp: P.SinglestepPlan, model_s=None, model_s1=None, keep=False,
-                        times_dev: Optional[List[torch.Tensor]] = None, alsig=None, t_inputs=None):
+                        times_dev: Optional[List[torch.Tensor]] = None, alsig=None, t_inputs=None,
+                        dup_last: bool = False):
         """Execute one singlestep update: one fused launch per model evaluation.
 
         Stage j converts the network output evaluated at (x_j, times[j]) and, in the same kernel,
@@ -515,7 +535,8 @@ class DPM_Solver:
                 if skip_update:
                     m_new, _ = self._post_model(raw, xe, td[j], als[j])
                 else:
-                    m_new, x_next = self._post_model(raw, xe, td[j], als[j], co, x, m1, m2, want_m=want)
+                    m_new, x_next = self._post_model(raw, xe, td[j], als[j], co, x, m1, m2, want_m=want,
+                                                     dup_out=(not last) or dup_last)
                 ms[j] = m_new
             xe = x_next
         return x_next, ms
@@ -645,6 +666,7 @@ class DPM_Solver:
         device = x.device
         intermediates = []
         ns = self.noise_schedule
+        self._xin_pair = None
         with torch.no_grad():
             x = self._state(x)
             sd = x.dtype
@@ -688,7 +710,7 @@ class DPM_Solver:
                     m2 = older[-2] if co.order >= 3 else None
                     want = order >= 2 and step < steps
                     m_new, x_new = self._post_model(raw, xe, ts_dev[step - 1], alsig[step - 1], co, x,
-                                                    m1, m2, want_m=want)
+                                                    m1, m2, want_m=want, dup_out=step < steps)
                     x = x_new
                     t = ts_dev[step]
                     if self.correcting_xt_fn is not None:
@@ -749,7 +771,8 @@ class DPM_Solver:
                     nt = len(sp.times)
                     td = [all_dev[k + j:k + j + 1] for j in range(nt)]
                     x, _ = self._run_singlestep(x, sp, times_dev=td, alsig=alsig[k:k + nt],
-                                                t_inputs=None if tin is None else [tin[k + j] for j in range(nt)])
+                                                t_inputs=None if tin is None else [tin[k + j] for j in range(nt)],
+                                                dup_last=step + 1 < len(plans))
                     k += nt
                     if self.correcting_xt_fn is not None:
                         x = self._state_like(self.correcting_xt_fn(x, outer_dev[step + 1], step), sd)

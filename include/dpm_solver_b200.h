@@ -97,6 +97,8 @@ typedef struct dpm_step_desc {
   const void* m2;
   void* m_out;     /* optional: computed model value written here (n_model >= 1)           */
   void* out;       /* x_t; required unless form == NONE                                    */
+  void* out2;      /* optional second copy of x_t (e.g. the other half of the network's
+                      doubled CFG batch, model_wrapper :326); NULL = none                   */
   /* model dtype tensors */
   const void* e_cond;   /* network output (conditional half under CFG)                     */
   const void* e_uncond; /* unconditional half, n_model == 2; CFG :329-330                  */

@@ -50,9 +50,9 @@ def test_argument_validation_needs_no_gpu():
 
 
 def test_struct_layout_matches_header():
-    """ctypes mirror of dpm_step_desc: 10 pointers, 2 u64, 8 i32, 12 floats."""
+    """ctypes mirror of dpm_step_desc: 11 pointers, 2 u64, 8 i32, 12 floats."""
     from dpm_solver_b200 import _lib
-    assert C.sizeof(_lib.StepDesc) == 10 * 8 + 2 * 8 + 8 * 4 + 12 * 4
+    assert C.sizeof(_lib.StepDesc) == 11 * 8 + 2 * 8 + 8 * 4 + 12 * 4
     src = open(os.path.join(ROOT, "include", "dpm_solver_b200.h")).read()
     body = src[src.index("typedef struct dpm_step_desc {"):src.index("} dpm_step_desc;")]
     names = re.findall(r"\b(\w+)\s*(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))

@@ -350,3 +350,20 @@ def test_constant_division_is_ieee(cuda_backend):
             ref = xm.cpu().numpy() / d
         bad += int((got.view(np.uint32) != ref.view(np.uint32)).sum())
     assert bad == 0
+
+
+@pytest.mark.parametrize("sdt", [torch.float32, torch.bfloat16])
+def test_second_output_copy(cuda_backend, sdt):
+    """out2 (the other half of the doubled CFG batch, model_wrapper :326) receives the same x_t."""
+    for n in (8 * 200000 + 3, 8 * 700):
+        for variant in (0, 1):
+            a = make_args(FORM_DIFF2, 2, n, sdt, sdt, predict_x0=True, seed=21)
+            ref_m, ref_o = OracleBackend().step(a)
+            d = to_dev(a)
+            buf = torch.empty(2 * n + 16, dtype=sdt, device=DEV)
+            d.out, d.out2 = buf[:n], buf[n:2 * n]          # for odd n the second half is misaligned
+            cuda_backend.set_tuning(variant, 0, 0)
+            m, o = cuda_backend.step(d)
+            cuda_backend.set_tuning(2, 0, 0)
+            assert o.data_ptr() == buf.data_ptr()
+            assert torch.equal(buf[:n].cpu(), ref_o) and torch.equal(buf[n:2 * n].cpu(), ref_o) and torch.equal(m.cpu(), ref_m)
