@@ -227,7 +227,7 @@ def make_timed_backend():
                 if t is not None and t.data_ptr() not in seen:
                     seen.add(t.data_ptr())
                     tot += n * t.element_size()
-            for t in (m_out, out):
+            for t in (m_out, out, a.out2):
                 if t is not None:
                     tot += n * t.element_size()
             return tot

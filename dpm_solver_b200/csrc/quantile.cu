@@ -36,7 +36,8 @@ constexpr int kQThreads = 512;      // cluster kernel
 constexpr int kBins = 2048;
 constexpr int kSamples = 1024;      // sample keys per sample (pivot kernel)
 constexpr int kPThreads = 256;      // pivot / count / finish kernels
-constexpr int kChunk = 8192;        // elements per CTA of the count kernel
+constexpr int kChunk = 8192;        // elements per CTA iteration of the count kernel
+constexpr int kIter = 4;            // consecutive chunks per CTA (amortises the per-CTA epilogue)
 constexpr int kLocalCand = 2048;    // bracket keys one count-CTA may collect
 
 struct QParams {
@@ -137,8 +138,16 @@ __global__ void __launch_bounds__(kPThreads) k_q_pivots(const __grid_constant__ 
   __shared__ uint32_t samp[kSamples];
   const uint64_t sample = blockIdx.x;
   const size_t s_begin = sample * p.per_sample;
-  for (int j = threadIdx.x; j < kSamples; j += kPThreads)
-    samp[j] = key_of_element<NE>(p, s_begin + (size_t)(((unsigned __int128)j * p.per_sample) / kSamples));
+  // 256 evenly strided groups of 4 consecutive elements: one 16/32-byte DRAM access serves 4 keys
+  // (a strided single-element gather moves a 128-byte line per key). Neighbouring elements of real
+  // images are correlated, so the bracket margin is sized for ~kSamples/4 independent draws.
+  for (int j = threadIdx.x; j < kSamples; j += kPThreads) {
+    const uint64_t grp = j >> 2;
+    uint64_t pos = (uint64_t)(((unsigned __int128)grp * p.per_sample) / (kSamples / 4));
+    pos = (pos & ~(uint64_t)3) + (j & 3);
+    if (pos >= p.per_sample) pos = p.per_sample - 1;
+    samp[j] = key_of_element<NE>(p, s_begin + pos);
+  }
   __syncthreads();
   for (int k = 2; k <= kSamples; k <<= 1) {       // bitonic sort, ascending
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -168,13 +177,9 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
                                                         const __grid_constant__ QParams qp) {
   __shared__ uint32_t lcand[kLocalCand];
   __shared__ uint32_t s_n, s_lt, s_base;
-  const uint32_t cps = qp.slice;                                   // chunks per sample
+  const uint32_t cps = qp.slice;                                   // CTAs per sample
   const uint64_t sample = blockIdx.x / cps;
-  const uint32_t chunk = blockIdx.x % cps;
-  const uint64_t c_begin = (uint64_t)chunk * kChunk;
-  const uint64_t c_end = c_begin + kChunk < p.per_sample ? c_begin + kChunk : p.per_sample;
-  const uint32_t cnt = (uint32_t)(c_end - c_begin);
-  const size_t e0 = sample * p.per_sample + c_begin;
+  const uint32_t part = blockIdx.x % cps;
   uint32_t* hdr = qp.work + sample * H_WORDS;
   const uint32_t lo_k = hdr[H_LO], hi_k = hdr[H_HI];
   const int tid = threadIdx.x;
@@ -189,36 +194,44 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
       if (pos < kLocalCand) lcand[pos] = k;
     }
   };
-  if (VEC) {
-    const TS* __restrict__ gxe = static_cast<const TS*>(p.xe);
-    const TE* __restrict__ gec = static_cast<const TE*>(p.ec);
-    const TE* __restrict__ geu = static_cast<const TE*>(p.eu);
-    const uint32_t npk = cnt / kPacket;                            // per_sample % 8 == 0 here
-    constexpr int U = kChunk / kPacket / kPThreads;                // 4 packets per thread
-    Raw<TS> rx[U];
-    Raw<TE> rc[U], ru[U];
+#pragma unroll 1
+  for (int it = 0; it < kIter; ++it) {
+    const uint64_t c_begin = ((uint64_t)part * kIter + it) * kChunk;
+    if (c_begin >= p.per_sample) break;
+    const uint64_t c_end = c_begin + kChunk < p.per_sample ? c_begin + kChunk : p.per_sample;
+    const uint32_t cnt = (uint32_t)(c_end - c_begin);
+    const size_t e0 = sample * p.per_sample + c_begin;
+    if (VEC) {
+      const TS* __restrict__ gxe = static_cast<const TS*>(p.xe);
+      const TE* __restrict__ gec = static_cast<const TE*>(p.ec);
+      const TE* __restrict__ geu = static_cast<const TE*>(p.eu);
+      const uint32_t npk = cnt / kPacket;                          // per_sample % 8 == 0 here
+      constexpr int U = kChunk / kPacket / kPThreads;              // 4 packets per thread
+      Raw<TS> rx[U];
+      Raw<TE> rc[U], ru[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t pk = u * kPThreads + tid;
-      if (pk < npk) {
-        const size_t e = e0 + (size_t)pk * kPacket;
-        ldg_pk(rx[u], gxe + e);
-        ldg_pk(rc[u], gec + e);
-        if (NE == 2) ldg_pk(ru[u], geu + e);
+      for (int u = 0; u < U; ++u) {
+        const uint32_t pk = u * kPThreads + tid;
+        if (pk < npk) {
+          const size_t e = e0 + (size_t)pk * kPacket;
+          ldg_pk(rx[u], gxe + e);
+          ldg_pk(rc[u], gec + e);
+          if (NE == 2) ldg_pk(ru[u], geu + e);
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t pk = u * kPThreads + tid;
-      if (pk < npk) {
-        uint32_t k8[8];
-        keys_of_packet<NE>(p, rx[u], rc[u], ru[u], k8);
+      for (int u = 0; u < U; ++u) {
+        const uint32_t pk = u * kPThreads + tid;
+        if (pk < npk) {
+          uint32_t k8[8];
+          keys_of_packet<NE>(p, rx[u], rc[u], ru[u], k8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) visit(k8[i]);
+          for (int i = 0; i < 8; ++i) visit(k8[i]);
+        }
       }
+    } else {
+      for (uint32_t i = tid; i < cnt; i += kPThreads) visit(key_of_element<NE>(p, e0 + i));
     }
-  } else {
-    for (uint32_t i = tid; i < cnt; i += kPThreads) visit(key_of_element<NE>(p, e0 + i));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c_lt += __shfl_xor_sync(0xffffffffu, c_lt, o);
@@ -527,9 +540,9 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
   if (want_pipeline && need != 0 && workspace != nullptr && workspace_bytes >= need &&
       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && ps < (1ull << 32)) {
     const double f = ps > 1 ? (double)qp.lo / (double)(ps - 1) : 0.0;
-    qp.margin = (int32_t)(4.0 * sqrt((double)kSamples * f * (1.0 - f)) + 3.0);
+    qp.margin = (int32_t)(8.0 * sqrt((double)kSamples * f * (1.0 - f)) + 3.0);   // 4 sigma at kSamples/4 effective draws
     qp.cap = pipeline_cap(ps);
-    qp.slice = (uint32_t)((ps + kChunk - 1) / kChunk);
+    qp.slice = (uint32_t)((ps + (uint64_t)kChunk * kIter - 1) / ((uint64_t)kChunk * kIter));
     qp.work = static_cast<uint32_t*>(workspace);
     if (n_samples * qp.slice > 0x7fffffffull) { set_error("too many chunks"); return DPM_ERR_UNSUPPORTED; }
     QKernel kp = p.n_model == 2 ? k_q_pivots<2> : k_q_pivots<1>;

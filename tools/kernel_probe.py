@@ -56,7 +56,7 @@ def build(form, n_model, sdt, mdt, n, sets=3, m_out=True, thr_ps=0):
 def algo_bytes(a):
     n = a.reference_tensor().numel()
     seen, tot = set(), 0
-    for t in (a.x, a.xe, a.m0, a.m1, a.m2, a.e_cond, a.e_uncond, a.m_out, a.out):
+    for t in (a.x, a.xe, a.m0, a.m1, a.m2, a.e_cond, a.e_uncond, a.m_out, a.out, a.out2):
         if t is not None and t.data_ptr() not in seen:
             seen.add(t.data_ptr())
             tot += n * t.element_size()
