@@ -178,8 +178,10 @@ class CudaBackend:
         if rc != 0:
             _lib.check(rc)
 
-    def dynamic_threshold(self, a: StepArgs, q: float, max_val: float) -> torch.Tensor:
-        """Per-sample s_b = max(quantile(|x0_b|, q), max_val) -> fp32 [B] (one launch)."""
+    def dynamic_threshold(self, a: StepArgs, q: float, max_val: float, return_stats: bool = False):
+        """Per-sample s_b = max(quantile(|x0_b|, q), max_val) -> fp32 [B].
+        return_stats=True also returns the pipeline's per-sample header words (int32 [B, 8]:
+        lo key, hi key, #below, #inside, path (1 bracket / 2 exact fallback), ...) for diagnostics."""
         d, keep, ref, _ = self._fill(a)
         if a.per_sample <= 0 or ref.numel() % a.per_sample:
             raise ValueError("dpm_solver_b200: per_sample must divide numel")
@@ -190,6 +192,9 @@ class CudaBackend:
         self._launch(ref.device, self._lib.dpm_dynamic_threshold, C.c_void_p(s.data_ptr()), C.byref(d),
                      C.c_float(q), C.c_float(max_val), C.c_void_p(ws.data_ptr() if ws is not None else None),
                      C.c_size_t(ws_bytes))
+        if return_stats:
+            hdr = ws[:nb * 32].view(torch.int32).reshape(nb, 8).clone() if ws is not None else None
+            return s, hdr
         return s
 
     def launch_count(self) -> int:
