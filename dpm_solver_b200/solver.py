@@ -322,36 +322,37 @@ class DPM_Solver:
         t_in = self._upload(w.get_model_input_time(t_host.reshape(-1)), device)   # (t - 1/N) * 1000, fp32, :278
         return t_in[:, None].expand(t_in.shape[0], w.input_rows(batch)).contiguous()
 
-    def _conv_args(self, raw: RawOutput, xe, alsig, sdtype) -> StepArgs:
-        """StepArgs fields that turn `raw` into the buffered model value at time t.
-        `alsig` is (alpha_t, sigma_t) from the plan, or the host time tensor to derive them from."""
+    def _conv_args(self, raw: RawOutput, xe, alsig, sdtype, x0: bool) -> StepArgs:
+        """StepArgs fields that turn `raw` into the buffered model value at time t (x0 if `x0`, else
+        eps). `alsig` is (alpha_t, sigma_t) from the plan, or the host time tensor to derive them."""
         a = StepArgs(n_model=2 if raw.e_uncond is not None else 1, e_cond=raw.e_cond,
                      e_uncond=raw.e_uncond, param=raw.param, guidance=raw.guidance,
-                     predict_x0=self._pp, state_dtype=sdtype)
-        if self._pp or raw.param != PARAM_NOISE:
+                     predict_x0=x0, state_dtype=sdtype)
+        if x0 or raw.param != PARAM_NOISE:
             a.alpha_e, a.sigma_e = alsig if isinstance(alsig, tuple) else self._alpha_sigma(alsig)
             a.xe = xe
         return a
 
-    def _needs_conversion(self, raw: RawOutput, sdtype) -> bool:
-        return (self._pp or raw.e_uncond is not None or raw.param != PARAM_NOISE
-                or raw.e_cond.dtype != sdtype)
+    @staticmethod
+    def _needs_conversion(raw: RawOutput, sdtype, x0: bool) -> bool:
+        return x0 or raw.e_uncond is not None or raw.param != PARAM_NOISE or raw.e_cond.dtype != sdtype
 
     def _post_model(self, raw: RawOutput, xe, t_dev, alsig, co: Optional[P.Coeffs] = None, x=None,
-                    m1=None, m2=None, want_m: bool = True, dup_out: bool = False):
+                    m1=None, m2=None, want_m: bool = True, dup_out: bool = False, x0: Optional[bool] = None):
         """The fused post-model step: buffered value from `raw` (+ optional update `co`).
 
         Returns (m_new, x_next). Falls back to two launches only when a user-supplied
         `correcting_x0_fn` must see the materialised x0 (:440-441)."""
         be = ops.backend()
+        x0 = self._pp if x0 is None else x0          # buffered value: x0 (dpmsolver++ / data_prediction_fn) or eps
         sd = xe.dtype if xe is not None else (x.dtype if x is not None else raw.e_cond.dtype)
-        custom_fix = self._pp and self.correcting_x0_fn is not None and not self._dynamic_thresholding
-        if not self._needs_conversion(raw, sd):
+        custom_fix = x0 and self.correcting_x0_fn is not None and not self._dynamic_thresholding
+        if not self._needs_conversion(raw, sd, x0):
             m_new = raw.e_cond if raw.e_cond.is_contiguous() else raw.e_cond.contiguous()
             x_next = self._pure_update(co, x, m_new, m1, m2) if co is not None else None
             return m_new, x_next
-        a = self._conv_args(raw, xe, alsig, sd)
-        if self._pp and self._dynamic_thresholding:
+        a = self._conv_args(raw, xe, alsig, sd, x0)
+        if x0 and self._dynamic_thresholding:
             a.per_sample = xe.numel() // xe.shape[0]
             a.thr = be.dynamic_threshold(a, float(self.dynamic_thresholding_ratio),
                                          float(self.thresholding_max_val))
@@ -409,16 +410,9 @@ class DPM_Solver:
 
     def data_prediction_fn(self, x, t):
         """x0 = (x - sigma_t*eps)/alpha_t with corrector (:433-442), one fused launch."""
-        if not self._pp:
-            # reference semantics regardless of algorithm_type
-            saved, self.algorithm_type = self.algorithm_type, "dpmsolver++"
-            try:
-                return self.data_prediction_fn(x, t)
-            finally:
-                self.algorithm_type = saved
         xs = self._state(x)
         raw = self._evaluate(xs, t)
-        return self._post_model(raw, xs, t, P._cpu(t)[:1])[0]
+        return self._post_model(raw, xs, t, P._cpu(t)[:1], x0=True)[0]   # x0 regardless of algorithm_type
 
     def model_fn(self, x, t):
         """Noise prediction (dpmsolver) or data prediction (dpmsolver++) (:444-451)."""
