@@ -1,0 +1,94 @@
+"""Randomised end-to-end parity against the UNMODIFIED reference (build container only).
+
+Draws sampling configurations at random (schedule, algorithm, method, order, steps, skip type,
+solver type, parameterisation, CFG, thresholding, t_end, denoise_to_zero), runs the reference on CPU
+and the product's host logic on the numpy executor, and requires bit-identical outputs and an
+identical trace of network calls. Complements the fixed golden cases of tests/golden/."""
+import os
+import random
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+REF = os.environ.get("DPM_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "dpm_solver_pytorch.py")),
+                                reason="reference tree not available")
+
+from cases import exact_net, make_betas, seeded  # noqa: E402
+
+
+def reference_module():
+    import importlib.util
+    warnings.filterwarnings("ignore")
+    spec = importlib.util.spec_from_file_location("_ref_dpm_solver_pytorch", os.path.join(REF, "dpm_solver_pytorch.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def draw(rng):
+    method = rng.choice(["multistep", "multistep", "singlestep", "singlestep_fixed"])
+    order = rng.choice([1, 2, 3])
+    steps = rng.randint(max(order, 3), 24)
+    c = dict(schedule=rng.choice(["sd", "ddpm_linear", "iddpm_cosine", "vp_linear"]),
+             algo=rng.choice(["dpmsolver++", "dpmsolver"]), method=method, order=order, steps=steps,
+             skip_type=rng.choice(["time_uniform", "logSNR", "time_quadratic"]),
+             solver_type=rng.choice(["dpmsolver", "taylor"]), model_type=rng.choice(["noise", "noise", "v", "x_start", "score"]),
+             cfg=rng.choice([None, None, 1.0, 3.5, 7.5]), lower_order_final=rng.choice([True, False]),
+             denoise_to_zero=rng.random() < 0.2, t_end=rng.choice([None, 1e-3, 0.02]), seed=rng.randint(0, 10 ** 6))
+    c["thresholding"] = c["algo"] == "dpmsolver++" and rng.random() < 0.25
+    if c["schedule"] == "vp_linear" and c["t_end"] is None:
+        c["t_end"] = 1e-3
+    return c
+
+
+def run(mod_ns, mod_wrap, mod_solver, c):
+    kind, betas = make_betas(c["schedule"])
+    ns = mod_ns("linear") if kind == "linear" else mod_ns("discrete", betas=torch.from_numpy(betas))
+    B = 2
+    x = seeded((B, 3, 8, 8), c["seed"])
+    calls = []
+    if c["cfg"] is not None:
+        def net(xx, tt, cc):
+            calls.append((float(tt[0]), tuple(xx.shape)))
+            return exact_net(xx, tt) + 0.05 * cc.reshape(-1, 1, 1, 1)
+        fn = mod_wrap(net, ns, model_type=c["model_type"], guidance_type="classifier-free", condition=torch.ones(B, 1),
+                      unconditional_condition=torch.zeros(B, 1), guidance_scale=c["cfg"])
+    else:
+        def net(xx, tt):
+            calls.append((float(tt[0]), tuple(xx.shape)))
+            return exact_net(xx, tt)
+        fn = mod_wrap(net, ns, model_type=c["model_type"])
+    s = mod_solver(fn, ns, algorithm_type=c["algo"], correcting_x0_fn="dynamic_thresholding" if c["thresholding"] else None)
+    y, inter = s.sample(x, steps=c["steps"], order=c["order"], skip_type=c["skip_type"], method=c["method"],
+                        lower_order_final=c["lower_order_final"], denoise_to_zero=c["denoise_to_zero"],
+                        solver_type=c["solver_type"], t_end=c["t_end"], return_intermediate=True)
+    return y, inter, calls
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_random_configurations_bit_exact(oracle_backend, chunk):
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    rng = random.Random(1000 + chunk)
+    done = 0
+    while done < 12:
+        c = draw(rng)
+        try:
+            yr, ir, cr = run(ref.NoiseScheduleVP, ref.model_wrapper, ref.DPM_Solver, c)
+        except Exception as e:   # configurations the reference itself rejects must be rejected the same way
+            with pytest.raises(type(e)):
+                run(new.NoiseScheduleVP, new.model_wrapper, new.DPM_Solver, c)
+            continue
+        if not torch.isfinite(yr).all():
+            continue
+        yn, in_, cn = run(new.NoiseScheduleVP, new.model_wrapper, new.DPM_Solver, c)
+        assert cn == cr, c
+        np.testing.assert_array_equal(yn.numpy(), yr.numpy(), err_msg=str(c))
+        assert len(in_) == len(ir), c
+        for a, b in zip(in_, ir):
+            np.testing.assert_array_equal(a.numpy(), b.numpy(), err_msg=str(c))
+        done += 1
