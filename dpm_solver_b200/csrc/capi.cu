@@ -202,6 +202,7 @@ static int finish(cudaStream_t) {
 static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   KParams p;
   Needs nd;
+  if (d != nullptr && d->n == 0) return DPM_OK;  // empty tensors: nothing to do (pointers may be NULL)
   int rc = build_params(d, &p, &nd, false);
   if (rc != DPM_OK) return rc;
   if (p.n == 0) return DPM_OK;
@@ -344,6 +345,7 @@ int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, floa
   if (!(q >= 0.f && q <= 1.f)) { set_error("q must be in [0,1]"); return DPM_ERR_ARG; }
   KParams p;
   Needs nd;
+  if (desc != nullptr && desc->n == 0) return DPM_OK;
   int rc = build_params(desc, &p, &nd, true);
   if (rc != DPM_OK) return rc;
   if (p.n == 0) return DPM_OK;
