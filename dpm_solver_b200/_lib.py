@@ -57,6 +57,8 @@ PROTOTYPES = {
     "dpm_data_prediction": (C.c_int, [_vp, _vp, _vp, _f, _f, _vp, _u64, _u64, _i, _vp]),
     "dpm_dynamic_threshold_workspace": (C.c_size_t, [_u64, _u64]),
     "dpm_dynamic_threshold": (C.c_int, [_vp, C.POINTER(StepDesc), _f, _f, _vp, C.c_size_t, _vp]),
+    "dpm_adaptive_error_workspace": (C.c_size_t, [_u64, _u64]),
+    "dpm_adaptive_error": (C.c_int, [_vp, _vp, _vp, _vp, _f, _f, _u64, _u64, _i, _vp, C.c_size_t, _vp]),
 }
 
 _lib = None

@@ -25,7 +25,7 @@ OUT_DIR = PKG / "lib"
 BUILD_DIR = PKG / "build"
 LIB_NAME = "libdpmsolver_b200.so"
 
-SOURCES = ["capi.cu", "step_direct.cu", "step_tma.cu", "quantile.cu"]
+SOURCES = ["capi.cu", "step_direct.cu", "step_tma.cu", "quantile.cu", "adaptive.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

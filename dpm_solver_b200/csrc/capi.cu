@@ -355,4 +355,19 @@ int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, floa
   return finish(static_cast<cudaStream_t>(stream));
 }
 
+size_t dpm_adaptive_error_workspace(uint64_t n, uint64_t per_sample) {
+  return adaptive_workspace_bytes(n, per_sample);
+}
+
+int dpm_adaptive_error(float* e_out, const void* x_higher, const void* x_lower, const void* x_prev, float atol,
+                       float rtol, uint64_t per_sample, uint64_t n, int dtype, void* workspace,
+                       size_t workspace_bytes, dpm_stream_t stream) {
+  if (!e_out || !x_higher || !x_lower || !x_prev) { set_error("adaptive error: NULL tensor"); return DPM_ERR_ARG; }
+  if (!valid_dtype(dtype) || per_sample == 0 || n == 0 || n % per_sample) { set_error("adaptive error: bad dtype or sizes"); return DPM_ERR_ARG; }
+  int rc = launch_adaptive_error(e_out, x_higher, x_lower, x_prev, atol, rtol, per_sample, n, dtype, workspace,
+                                 workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (rc != DPM_OK) return rc;
+  return finish(static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -28,5 +28,8 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream);
 int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q, float max_val,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t quantile_workspace_bytes(uint64_t n_samples, uint64_t per_sample);
+size_t adaptive_workspace_bytes(uint64_t n, uint64_t per_sample);
+int launch_adaptive_error(float* out, const void* xh, const void* xl, const void* xp, float atol, float rtol,
+                          uint64_t per_sample, uint64_t n, int dtype, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace dpm

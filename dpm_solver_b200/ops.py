@@ -197,6 +197,20 @@ class CudaBackend:
             return s, hdr
         return s
 
+    def error_norm(self, x_higher, x_lower, x_prev, atol: float, rtol: float) -> torch.Tensor:
+        """E of dpm_solver_adaptive (:999-1001) as a device fp32 tensor of shape (1,)."""
+        n, dev = x_higher.numel(), x_higher.device
+        ts = [self._check(t, w, dev, n, x_higher.dtype) for t, w in ((x_higher, "x_higher"), (x_lower, "x_lower"), (x_prev, "x_prev"))]
+        per_sample = n // x_higher.shape[0]
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws_bytes = int(self._lib.dpm_adaptive_error_workspace(n, per_sample))
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+        self._launch(dev, self._lib.dpm_adaptive_error, C.c_void_p(out.data_ptr()), C.c_void_p(ts[0].data_ptr()),
+                     C.c_void_p(ts[1].data_ptr()), C.c_void_p(ts[2].data_ptr()), C.c_float(atol), C.c_float(rtol),
+                     C.c_uint64(per_sample), C.c_uint64(n), C.c_int(_DTYPE_CODE[x_higher.dtype]),
+                     C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes))
+        return out
+
     def launch_count(self) -> int:
         return int(self._lib.dpm_launch_count())
 

@@ -578,8 +578,8 @@ class DPM_Solver:
     # -- adaptive solver (:956-1010) ---------------------------------------------------------------
     def dpm_solver_adaptive(self, x, order, t_T, t_0, h_init=0.05, atol=0.0078, rtol=0.05, theta=0.9,
                             t_err=1e-5, solver_type='dpmsolver'):
-        """Adaptive step size DPM-Solver-12 / -23. The updates run on the fused kernels; the
-        error-norm reduction (:999-1001) still uses torch reductions (scheduled: SURVEY 8f-2)."""
+        """Adaptive step size DPM-Solver-12 / -23 (:956-1010). Updates and the error estimate run on
+        the fused kernels; the step-size controller is the reference's host logic."""
         ns = self.noise_schedule
         x = self._state(x)
         s = t_T * torch.ones((1,))
@@ -605,10 +605,9 @@ class DPM_Solver:
             t = ns.inverse_lambda(lambda_s + h)
             x_lower, lower_noise_kwargs = lower_update(x, s, t)
             x_higher = higher_update(x, s, t, **lower_noise_kwargs)
-            xl, xh, xp = x_lower.float(), x_higher.float(), x_prev.float()
-            delta = torch.max(torch.ones_like(xl) * atol, rtol * torch.max(torch.abs(xl), torch.abs(xp)))
-            norm_fn = lambda v: torch.sqrt(torch.square(v.reshape((v.shape[0], -1))).mean(dim=-1, keepdim=True))
-            E = norm_fn((xh - xl) / delta).max().cpu()
+            # E = max_b sqrt(mean(((x_higher - x_lower)/delta)^2)), delta = max(atol, rtol*max(|x_lower|,|x_prev|))
+            # (:999-1001): one fused reduction launch; the accept/reject test needs E on the host (:1002)
+            E = ops.backend().error_norm(x_higher, x_lower, self._state_like(x_prev, x_higher.dtype), atol, rtol).cpu()
             if torch.all(E <= 1.):
                 x = x_higher
                 s = t

@@ -204,6 +204,17 @@ DPM_API size_t dpm_dynamic_threshold_workspace(uint64_t n_samples, uint64_t per_
 DPM_API int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, float max_val,
                                   void* workspace, size_t workspace_bytes, dpm_stream_t stream);
 
+/* DPM_Solver.dpm_solver_adaptive error estimate :999-1001:
+ *   delta = max(atol, rtol*max(|x_lower|, |x_prev|));
+ *   E = max over samples of sqrt(mean(((x_higher - x_lower)/delta)^2))  ->  e_out[0] (device fp32).
+ * One streaming pass + a one-CTA epilogue, deterministic reduction order. workspace: device memory
+ * of dpm_adaptive_error_workspace(n, per_sample) bytes. */
+DPM_API size_t dpm_adaptive_error_workspace(uint64_t n, uint64_t per_sample);
+DPM_API int dpm_adaptive_error(float* e_out, const void* x_higher, const void* x_lower,
+                               const void* x_prev, float atol, float rtol, uint64_t per_sample,
+                               uint64_t n, int dtype, void* workspace, size_t workspace_bytes,
+                               dpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,7 +199,34 @@ def gen_samples():
     return len(out)
 
 
+ADAPTIVE_CASES = [
+    dict(name="ad23_eps_vp", schedule="vp_linear", algo="dpmsolver", order=3, t_end=1e-3, solver_type="dpmsolver"),
+    dict(name="ad12_eps_vp", schedule="vp_linear", algo="dpmsolver", order=2, t_end=1e-3, solver_type="dpmsolver"),
+    dict(name="ad23_pp_sd", schedule="sd", algo="dpmsolver++", order=3, t_end=None, solver_type="taylor"),
+    dict(name="ad12_pp_sd", schedule="sd", algo="dpmsolver++", order=2, t_end=None, solver_type="dpmsolver"),
+]
+
+
+def gen_adaptive():
+    """dpm_solver_adaptive (:956-1010): final sample and NFE (the reference prints it)."""
+    import contextlib
+    import io
+    out = {}
+    for c in ADAPTIVE_CASES:
+        ns = build_schedule(c["schedule"])
+        x = seeded((2, 3, 8, 8), 77)
+        s = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type=c["algo"])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            y = s.sample(x, method="adaptive", order=c["order"], t_end=c["t_end"], solver_type=c["solver_type"])
+        out[c["name"] + "/y"] = np32(y)
+        out[c["name"] + "/nfe"] = np.asarray(int(buf.getvalue().split()[-1]))
+    np.savez_compressed(os.path.join(HERE, "adaptive.npz"), **out)
+    return len(out)
+
+
 if __name__ == "__main__":
+    print("adaptive", gen_adaptive())
     print("schedules", gen_schedules())
     print("updates", gen_updates())
     print("glue", gen_glue())

@@ -126,6 +126,15 @@ class OracleBackend:
                 a.out2.copy_(out.reshape(a.out2.shape))
         return m_out, out
 
+    def error_norm(self, x_higher, x_lower, x_prev, atol, rtol):
+        """dpm_solver_adaptive :999-1001 in numpy fp32."""
+        self.launches += 1
+        xh, xl, xp = _np(x_higher), _np(x_lower), _np(x_prev)
+        delta = np.maximum(f32(atol), f32(rtol) * np.maximum(np.abs(xl), np.abs(xp)))
+        v = ((xh - xl) / delta).reshape(xh.shape[0], -1)
+        e = np.sqrt(np.mean(np.square(v), axis=-1, dtype=np.float32))
+        return torch.tensor([float(e.max())], dtype=torch.float32)
+
     def dynamic_threshold(self, a, q, max_val):
         self.launches += 1
         self.log.append(("quantile", a.n_model))
