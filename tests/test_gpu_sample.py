@@ -104,3 +104,44 @@ def test_adaptive_runs(cuda_backend, capsys):
     x = torch.randn(2, 3, 8, 8, device="cuda:0")
     y = s.sample(x, method="adaptive", order=3, t_end=1e-3)
     assert torch.isfinite(y).all() and "adaptive solver nfe" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("name", ["pp2m", "eps3s_cfg", "pp3m_thr"])
+def test_whole_sample_loop_is_cuda_graph_capturable(golden, cuda_backend, name):
+    """once the plan and the device tables are cached (first call), sample() issues no
+    host<->device copy, no sync and no collective, so the whole loop -- network calls included, if
+    the network is capturable -- can be captured in one CUDA graph and replayed."""
+    from cases import exact_net, make_betas, seeded
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    from helpers import product_schedule
+    case = CASES[name]
+    ns = product_schedule(case["schedule"])
+    B = case["shape"][0]
+    x = seeded(case["shape"], case["seed"]).cuda()
+    if case.get("cfg"):
+        net = lambda xx, tt, cc: exact_net(xx, tt) + 0.05 * cc.reshape(-1, 1, 1, 1)
+        fn = model_wrapper(net, ns, guidance_type="classifier-free", condition=torch.ones(B, 1, device="cuda"),
+                           unconditional_condition=torch.zeros(B, 1, device="cuda"), guidance_scale=case["cfg"])
+    else:
+        fn = model_wrapper(exact_net, ns)
+    s = DPM_Solver(fn, ns, algorithm_type=case["algo"],
+                   correcting_x0_fn="dynamic_thresholding" if case.get("thresholding") else None)
+    kw = dict(steps=case["steps"], order=case["order"], skip_type=case["skip_type"], method=case["method"])
+    y_eager = s.sample(x, **kw)                      # warms the plan / table caches
+    x_static = x.clone()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        s.sample(x_static, **kw)                     # warm-up on the capture stream
+        with torch.cuda.graph(g, stream=side):
+            y_static = s.sample(x_static, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_static, y_eager)
+    np.testing.assert_array_equal(y_static.cpu().numpy(), golden["samples"][f"{name}/y"])
+    x_static.copy_(x * 0.5)                          # new input, same graph
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_static, s.sample(x * 0.5, **kw))
