@@ -94,11 +94,12 @@ class NoiseScheduleVP:
         """(t, log_alpha, flipped log_alpha, flipped t) as 1-D tensors on `device` (cached)."""
         key = str(device)
         tab = self._tables.get(key)
-        if tab is None or tab[4] is not self.log_alpha_array or tab[5] is not self.t_array:
+        ver = (self.log_alpha_array._version, self.t_array._version)
+        if tab is None or tab[4] is not self.log_alpha_array or tab[5] is not self.t_array or tab[6] != ver:
             t = self.t_array.to(device).reshape(-1)
             la = self.log_alpha_array.to(device).reshape(-1)
             tab = (t.contiguous(), la.contiguous(), torch.flip(la, [0]).contiguous(),
-                   torch.flip(t, [0]).contiguous(), self.log_alpha_array, self.t_array)
+                   torch.flip(t, [0]).contiguous(), self.log_alpha_array, self.t_array, ver)
             self._tables[key] = tab
         return tab
 

@@ -272,10 +272,21 @@ class DPM_Solver:
     _CACHE_MAX = 16
 
     def _schedule_key(self):
+        """Identity of the schedule the cached plans were computed from. The table tensors are pinned
+        in `_schedule_refs` so their ids cannot be recycled; `_version` catches in-place edits."""
         ns = self.noise_schedule
         if getattr(ns, "schedule", None) == "discrete":
-            return ("discrete", id(ns.log_alpha_array), id(ns.t_array), ns.total_N)
-        return (getattr(ns, "schedule", None), getattr(ns, "beta_0", None), getattr(ns, "beta_1", None), id(ns))
+            la, ta = ns.log_alpha_array, ns.t_array
+            refs = self.__dict__.setdefault("_schedule_refs", {})
+            refs[id(la)], refs[id(ta)] = la, ta
+            if len(refs) > 64:
+                for k in list(refs)[:-8]:
+                    refs.pop(k)
+                for name in ("_plan_cache", "_table_cache", "_synced_cache"):
+                    self.__dict__.pop(name, None)
+            return ("discrete", id(la), la._version, id(ta), ta._version, ns.total_N)
+        return (getattr(ns, "schedule", None), getattr(ns, "beta_0", None), getattr(ns, "beta_1", None),
+                getattr(ns, "T", None))
 
     def _host_plan(self, key, build):
         """Coefficient plan of a run, cached per (schedule, algorithm, sampling arguments): repeated

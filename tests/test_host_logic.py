@@ -245,3 +245,28 @@ def test_hooks_and_custom_corrector(oracle_backend):
     y = s.sample(x, steps=6, order=2)
     assert [st for _, st in seen] == list(range(0, 7))
     assert torch.isfinite(y).all()
+
+
+def test_plan_cache_follows_the_schedule(oracle_backend):
+    """The cached coefficient plan is keyed on the schedule tables: replacing or editing them in
+    place must not serve a stale plan; repeated calls with one configuration reuse it."""
+    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper
+    from cases import exact_net, make_betas, seeded
+    ns = NoiseScheduleVP("discrete", betas=torch.from_numpy(make_betas("sd")[1]))
+    s = DPM_Solver(model_wrapper(exact_net, ns), ns)
+    x = seeded((2, 4, 8, 8), 9)
+    y1 = s.sample(x, steps=10, order=2)
+    assert len(s._plan_cache) == 1
+    y1b = s.sample(x, steps=10, order=2)
+    assert len(s._plan_cache) == 1 and torch.equal(y1, y1b)
+    s.sample(x, steps=10, order=3)
+    assert len(s._plan_cache) == 2
+    # other schedule tables -> a fresh solver on them gives the same answer as the cached one must now give
+    ns2 = NoiseScheduleVP("discrete", betas=torch.from_numpy(make_betas("ddpm_linear")[1]))
+    ns.log_alpha_array, ns.t_array, ns.total_N = ns2.log_alpha_array, ns2.t_array, ns2.total_N
+    y2 = s.sample(x, steps=10, order=2)
+    ref = DPM_Solver(model_wrapper(exact_net, ns2), ns2).sample(x, steps=10, order=2)
+    assert torch.equal(y2, ref) and not torch.equal(y2, y1)
+    ns.log_alpha_array.mul_(1.01)                     # in-place edit
+    y3 = s.sample(x, steps=10, order=2)
+    assert not torch.equal(y3, y2)
