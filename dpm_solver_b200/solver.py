@@ -593,29 +593,32 @@ class DPM_Solver:
         the fused kernels; the step-size controller is the reference's host logic."""
         ns = self.noise_schedule
         x = self._state(x)
+        device = x.device
+        # the controller's scalars live on the host (fp32, reference op order); the network receives
+        # device time labels, uploaded once per iteration
         s = t_T * torch.ones((1,))
         lambda_s = ns.marginal_lambda(s)
         lambda_0 = ns.marginal_lambda(t_0 * torch.ones_like(s))
         h = h_init * torch.ones_like(s)
         x_prev = x
         nfe = 0
-        if order == 2:
-            r1 = 0.5
-            lower_update = lambda x, s, t: self.dpm_solver_first_update(x, s, t, return_intermediate=True)
-            higher_update = lambda x, s, t, **kwargs: self.singlestep_dpm_solver_second_update(
-                x, s, t, r1=r1, solver_type=solver_type, **kwargs)
-        elif order == 3:
-            r1, r2 = 1. / 3., 2. / 3.
-            lower_update = lambda x, s, t: self.singlestep_dpm_solver_second_update(
-                x, s, t, r1=r1, return_intermediate=True, solver_type=solver_type)
-            higher_update = lambda x, s, t, **kwargs: self.singlestep_dpm_solver_third_update(
-                x, s, t, r1=r1, r2=r2, solver_type=solver_type, **kwargs)
-        else:
+        if order not in (2, 3):
             raise ValueError("For adaptive step size solver, order must be 2 or 3, got {}".format(order))
+        if solver_type not in ['dpmsolver', 'taylor']:
+            raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
         while torch.abs((s - t_0)).mean() > t_err:
             t = ns.inverse_lambda(lambda_s + h)
-            x_lower, lower_noise_kwargs = lower_update(x, s, t)
-            x_higher = higher_update(x, s, t, **lower_noise_kwargs)
+            if order == 2:      # DPM-Solver-12 (:985-988)
+                sp_low = P.SinglestepPlan(1, [P._cpu(s)], [P.first_update_coeffs(ns, self.algorithm_type, s, t)])
+                sp_high = P.singlestep_second(ns, self.algorithm_type, solver_type, s, t, 0.5)
+            else:               # DPM-Solver-23 (:989-992)
+                sp_low = P.singlestep_second(ns, self.algorithm_type, solver_type, s, t, 1. / 3.)
+                sp_high = P.singlestep_third(ns, self.algorithm_type, solver_type, s, t, 1. / 3., 2. / 3.)
+            t_all = self._upload(torch.cat([tt.reshape(-1) for tt in sp_high.times]), device)
+            td = [t_all[j:j + 1] for j in range(len(sp_high.times))]
+            x_lower, ms = self._run_singlestep(x, sp_low, keep=True, times_dev=td[:len(sp_low.times)])
+            x_higher, _ = self._run_singlestep(x, sp_high, model_s=ms[0], model_s1=ms[1] if order == 3 else None,
+                                               times_dev=td)
             # E = max_b sqrt(mean(((x_higher - x_lower)/delta)^2)), delta = max(atol, rtol*max(|x_lower|,|x_prev|))
             # (:999-1001): one fused reduction launch; the accept/reject test needs E on the host (:1002)
             E = ops.backend().error_norm(x_higher, x_lower, self._state_like(x_prev, x_higher.dtype), atol, rtol).cpu()
