@@ -94,7 +94,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -426,10 +426,12 @@ def run_b200(args, w):
     e2e_loop(2)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    e2e_loop(args.steps)
-    e3.record()
-    barrier()
+    with ClockSampler(local) as clk2:
+        e2.record()
+        e2e_loop(args.steps)
+        e3.record()
+        barrier()
+    clk.rows += clk2.rows
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     e2e_val = world * E * n_updates(w) * args.steps / (ms_e2e * 1e-3) / 1e9
     checksum = float(y_host[(args.steps - 1) % n_buf].float().abs().mean())
