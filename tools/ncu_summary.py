@@ -67,7 +67,11 @@ def main():
             g = lambda k: float(d[k][0].replace(",", "")) if k in d else float("nan")
             t = g("gpu__time_duration.sum")
             unit = d.get("gpu__time_duration.sum", ("", "us"))[1]
-            t_us = t / 1e3 if unit.startswith("ns") else t
+            t_us = {"ns": t / 1e3, "us": t, "ms": t * 1e3, "s": t * 1e6}.get(unit.replace("second", "s").replace("usecond", "us"), t)
+            if unit.startswith("ns"):
+                t_us = t / 1e3
+            elif unit.startswith("ms"):
+                t_us = t * 1e3
             rd, wr = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
             scale = lambda k: {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(d.get(k, ("", "byte"))[1], 1.0)
             rdb, wrb = rd * scale("dram__bytes_read.sum"), wr * scale("dram__bytes_write.sum")
