@@ -658,6 +658,39 @@ class DPM_Solver:
                            method=method, lower_order_final=lower_order_final, denoise_to_zero=denoise_to_zero,
                            solver_type=solver_type, atol=atol, rtol=rtol, return_intermediate=return_intermediate)
 
+    # -- whole-loop CUDA graph (no counterpart in the reference) -----------------------
+    def capture(self, x_example, **sample_kwargs):
+        """Capture `sample(x, **sample_kwargs)` -- the network calls included -- in ONE CUDA graph.
+
+        Once the coefficient plan and the device tables are cached, the sampling loop performs no
+        host<->device copy, no synchronisation and no collective, and every kernel takes its scalars
+        by value, so the whole run is capturable whenever the network is. Returns a callable
+        `g(x) -> x_0` that copies `x` into the graph's static input and replays; the returned tensor
+        is the graph's static output (clone it to keep it across replays). Not available for the
+        adaptive method (host-side accept/reject) or with python-side hooks that synchronise."""
+        if sample_kwargs.get("method", "multistep") == "adaptive":
+            raise ValueError("the adaptive solver decides on the host every iteration; it cannot be captured")
+        if sample_kwargs.get("return_intermediate"):
+            raise ValueError("capture() returns the final sample only")
+        x_static = self._state(x_example).clone()
+        self.sample(x_static, **sample_kwargs)                       # builds and caches plan + tables
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=x_static.device)
+        side.wait_stream(torch.cuda.current_stream(x_static.device))
+        with torch.cuda.stream(side):
+            self.sample(x_static, **sample_kwargs)                   # warm-up on the capture stream
+            with torch.cuda.graph(graph, stream=side):
+                y_static = self.sample(x_static, **sample_kwargs)
+        torch.cuda.current_stream(x_static.device).wait_stream(side)
+
+        def replay(x):
+            x_static.copy_(x)
+            graph.replay()
+            return y_static
+
+        replay.graph, replay.static_input, replay.static_output = graph, x_static, y_static
+        return replay
+
     # -- sample (:1047-1245) ---------------------------------------------------------------------
     def sample(self, x, steps=20, t_start=None, t_end=None, order=2, skip_type='time_uniform',
                method='multistep', lower_order_final=True, denoise_to_zero=False, solver_type='dpmsolver',

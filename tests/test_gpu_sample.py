@@ -145,3 +145,22 @@ def test_whole_sample_loop_is_cuda_graph_capturable(golden, cuda_backend, name):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(y_static, s.sample(x * 0.5, **kw))
+
+
+def test_capture_api(golden, cuda_backend):
+    """DPM_Solver.capture(): one graph launch per sample() -- zero per-step host work."""
+    from cases import exact_net, seeded
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    from helpers import product_schedule
+    ns = product_schedule("sd")
+    s = DPM_Solver(model_wrapper(exact_net, ns), ns)
+    x = seeded((2, 4, 16, 16), 1234).cuda()
+    run = s.capture(x, steps=20, order=2)
+    before = cuda_backend.launch_count()
+    y = run(x).clone()
+    assert cuda_backend.launch_count() == before          # replay launches nothing through the host path
+    np.testing.assert_array_equal(y.cpu().numpy(), golden["samples"]["pp2m/y"])
+    y2 = run(x * 0.25).clone()
+    assert torch.equal(y2, s.sample(x * 0.25, steps=20, order=2))
+    with pytest.raises(ValueError):
+        s.capture(x, method="adaptive")
