@@ -211,7 +211,7 @@ __device__ __forceinline__ float div_const(float x, float d, float r) {
   e = fmaf(-q, d, x);
   q = fmaf(e, r, q);
   const float ax = fabsf(x);
-  if (!(ax > 1e-30f && ax < 1e30f)) q = x / d;  // zero, denormal-range, huge, inf, nan: IEEE path
+  if (!(ax > 1e-25f && ax < 1e30f)) q = x / d;  // zero, tiny, huge, inf, nan: IEEE path
   return q;
 }
 // packet form: one range guard (and one cold IEEE block) per 8 elements instead of per element
@@ -226,7 +226,7 @@ __device__ __forceinline__ void div_const8(float (&x)[8], float d, float r) {
     e = fmaf(-t, d, x[i]);
     q[i] = fmaf(e, r, t);
     const float ax = fabsf(x[i]);
-    bad |= !(ax > 1e-30f && ax < 1e30f);
+    bad |= !(ax > 1e-25f && ax < 1e30f);
   }
   if (bad) {
 #pragma unroll
@@ -236,7 +236,8 @@ __device__ __forceinline__ void div_const8(float (&x)[8], float d, float r) {
   for (int i = 0; i < 8; ++i) x[i] = q[i];
 }
 __host__ __device__ __forceinline__ bool recip_div_ok(float d) {
-  // normal, finite, not too extreme, significand not all ones
+  // |d| within 2^-20 .. 2^20 (so that with 1e-25 < |x| < 1e30 neither the quotient nor the residual
+  // of div_const can overflow or reach the denormal range), significand not all ones
 #ifdef __CUDA_ARCH__
   const uint32_t b = __float_as_uint(d);
 #else
@@ -244,7 +245,7 @@ __host__ __device__ __forceinline__ bool recip_div_ok(float d) {
   memcpy(&b, &d, 4);
 #endif
   const uint32_t ex = (b >> 23) & 0xffu;
-  return ex > 40u && ex < 210u && (b & 0x7fffffu) != 0x7fffffu;
+  return ex >= 107u && ex <= 147u && (b & 0x7fffffu) != 0x7fffffu;
 }
 
 // ---- per-element arithmetic -----------------------------------------------------------------

@@ -325,12 +325,12 @@ def test_constant_division_is_ieee(cuda_backend):
     expo = torch.randint(-30, 30, (n,), device=DEV, generator=g).float()
     sign = torch.randint(0, 2, (n,), device=DEV, generator=g).float() * 2 - 1
     x = (sign * mant * torch.exp2(expo)).contiguous()
-    special = torch.tensor([0.0, -0.0, 1e-38, -1e-39, 1e-45, 3e38, -3e38, 1.0, 2.0, 0.5, 1.0000001, 0.99999994],
-                           device=DEV)
+    special = torch.tensor([0.0, -0.0, 1e-38, -1e-39, 1e-45, 3e38, -3e38, 1.0, 2.0, 0.5, 1.0000001, 0.99999994,
+                            1e-26, -3e-25, 9.9e-26, 1.1e-25, 9e29, 1.1e30, float("inf"), -float("inf")], device=DEV)
     x[:special.numel()] = special
     zeros = torch.zeros_like(x)
     rs = np.random.RandomState(3)
-    divisors = np.concatenate([rs.uniform(1e-3, 1.0, 150), rs.uniform(1.0, 40.0, 40),
+    divisors = np.concatenate([rs.uniform(1e-3, 1.0, 150), rs.uniform(1.0, 40.0, 40), [1e-7, 3e-6, 2e6, 1e-30, 1e20],
                                [1.0, 0.5, 0.25, 2.0, 0.99999994, 1.0000001, 0.0029151, 0.9998, 0.33333334,
                                 np.float32(1) - np.float32(2 ** -24), 1.9999999]]).astype(np.float32)
     xe = x.cpu().numpy()
