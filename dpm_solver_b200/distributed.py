@@ -10,7 +10,6 @@ buffered model values never leave their GPU.
 """
 from __future__ import annotations
 
-from dataclasses import fields
 from typing import List, Optional, Sequence
 
 import torch

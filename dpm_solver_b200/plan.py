@@ -14,7 +14,7 @@ bit-identical to the reference evaluated on CPU. All `t` arguments are 1-D fp32 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional, Union
 
 import torch
 

@@ -23,9 +23,8 @@ from typing import List, Optional
 import torch
 
 from . import ops, plan as P
-from ._lib import (FORM_DIFF2, FORM_LIN1, FORM_NONE, FORM_SS3T, PARAM_BY_NAME, PARAM_NOISE)
+from ._lib import FORM_LIN1, FORM_NONE, FORM_SS3T, PARAM_BY_NAME, PARAM_NOISE
 from .ops import StepArgs
-from .schedule import NoiseScheduleVP, expand_dims
 
 __all__ = ["model_wrapper", "DPM_Solver", "WrappedModel"]
 
