@@ -85,7 +85,19 @@ class CudaBackend:
 
     # -- helpers --------------------------------------------------------------------------
     @staticmethod
-    def _check(t: torch.Tensor, what: str, dev, numel: int, dtype=None) -> torch.Tensor:
+    def _layout(t: torch.Tensor) -> Optional[str]:
+        """'c' (row-major dense), 'cl' (channels_last dense) or None (needs a copy). Element-wise
+        kernels only need every operand to share ONE dense layout: the storage is then a flat array."""
+        if t.is_contiguous():
+            return "c"
+        if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+            return "cl"
+        if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
+            return "cl"
+        return None
+
+    @staticmethod
+    def _check(t: torch.Tensor, what: str, dev, numel: int, dtype=None, layout: str = "c") -> torch.Tensor:
         if not t.is_cuda:
             raise RuntimeError(f"dpm_solver_b200: `{what}` is on {t.device}; this library is CUDA-only "
                                "(no CPU fallback)")
@@ -97,6 +109,11 @@ class CudaBackend:
             raise TypeError(f"dpm_solver_b200: `{what}` is {t.dtype}, expected {dtype}")
         if t.dtype not in _DTYPE_CODE:
             raise TypeError(f"dpm_solver_b200: unsupported dtype {t.dtype} for `{what}`")
+        if layout == "cl":
+            if t.dim() in (4, 5) and t.is_contiguous(memory_format=torch.channels_last if t.dim() == 4 else torch.channels_last_3d):
+                return t
+            return t.contiguous(memory_format=torch.channels_last if t.dim() == 4 else torch.channels_last_3d) \
+                if t.dim() in (4, 5) else t.contiguous()
         return t if t.is_contiguous() else t.contiguous()
 
     def _fill(self, a: StepArgs):
@@ -106,13 +123,18 @@ class CudaBackend:
         if sdt is None:
             st = a.state_tensors()
             sdt = st[0].dtype if st else a.e_cond.dtype
-        keep = []  # keep contiguous copies alive until after the launch
+        # channels_last networks hand over channels_last tensors: keep that layout end to end
+        layout = self._layout(ref) or "c"
+        for t in (a.out, a.m_out, a.out2):
+            if t is not None and self._layout(t) != layout:
+                layout = "c"   # preallocated row-major outputs: bring the inputs to that layout
+        keep = []  # keep converted copies alive until after the launch
         d = StepDesc()
 
         def ptr(t, what, dtype):
             if t is None:
                 return None
-            t = self._check(t, what, dev, n, dtype)
+            t = self._check(t, what, dev, n, dtype, layout)
             keep.append(t)
             return t.data_ptr()
 
@@ -140,7 +162,14 @@ class CudaBackend:
         d.guidance, d.alpha_e, d.sigma_e = a.guidance, a.alpha_e, a.sigma_e
         d.a, d.c0, d.c1, d.c2 = a.a, a.c0, a.c1, a.c2
         d.w0, d.w1, d.w2, d.w3, d.w4 = a.w0, a.w1, a.w2, a.w3, a.w4
+        self._last_layout = layout
         return d, keep, ref, sdt
+
+    def _new_like(self, ref, sdt, layout):
+        if layout == "cl":
+            return torch.empty(ref.shape, dtype=sdt, device=ref.device,
+                               memory_format=torch.channels_last if ref.dim() == 4 else torch.channels_last_3d)
+        return torch.empty(ref.shape, dtype=sdt, device=ref.device)
 
     # -- API -----------------------------------------------------------------------------
     def step(self, a: StepArgs) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
@@ -148,16 +177,16 @@ class CudaBackend:
         d, keep, ref, sdt = self._fill(a)
         m_out = out = None
         if a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE):
-            m_out = a.m_out if a.m_out is not None else torch.empty(ref.shape, dtype=sdt, device=ref.device)
+            m_out = a.m_out if a.m_out is not None else self._new_like(ref, sdt, self._last_layout)
             self._check(m_out, "m_out", ref.device, ref.numel(), sdt)
-            if not m_out.is_contiguous():
-                raise ValueError("dpm_solver_b200: preallocated m_out must be contiguous")
+            if self._layout(m_out) != self._last_layout:
+                raise ValueError("dpm_solver_b200: preallocated m_out must be dense and laid out like the inputs")
             d.m_out = m_out.data_ptr()
         if a.form != FORM_NONE:
-            out = a.out if a.out is not None else torch.empty(ref.shape, dtype=sdt, device=ref.device)
+            out = a.out if a.out is not None else self._new_like(ref, sdt, self._last_layout)
             self._check(out, "out", ref.device, ref.numel(), sdt)
-            if not out.is_contiguous():
-                raise ValueError("dpm_solver_b200: preallocated out must be contiguous")
+            if self._layout(out) != self._last_layout:
+                raise ValueError("dpm_solver_b200: preallocated out must be dense and laid out like the inputs")
             d.out = out.data_ptr()
             if a.out2 is not None:
                 self._check(a.out2, "out2", ref.device, ref.numel(), sdt)

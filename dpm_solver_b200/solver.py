@@ -242,7 +242,7 @@ class DPM_Solver:
         sd = self._sdtype(x)
         if x.dtype != sd:
             x = x.to(sd)
-        return x if x.is_contiguous() else x.contiguous()
+        return x if ops.CudaBackend._layout(x) is not None else x.contiguous()
 
     def _alpha_sigma(self, t_host):
         ns = self.noise_schedule
@@ -265,7 +265,12 @@ class DPM_Solver:
         w = self._wrapped
         if self.correcting_xt_fn is not None or not (isinstance(w, WrappedModel) and w.fusable and w.uses_cfg):
             return None
-        x_in = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        shape = (2 * x.shape[0],) + tuple(x.shape[1:])
+        if ops.CudaBackend._layout(x) == "cl":      # keep a channels_last network's layout
+            x_in = torch.empty(shape, dtype=x.dtype, device=x.device,
+                               memory_format=torch.channels_last if x.dim() == 4 else torch.channels_last_3d)
+        else:
+            x_in = torch.empty(shape, dtype=x.dtype, device=x.device)
         return x_in, x_in[:x.shape[0]], x_in[x.shape[0]:]
 
     _CACHE_MAX = 16
@@ -358,7 +363,7 @@ class DPM_Solver:
         sd = xe.dtype if xe is not None else (x.dtype if x is not None else raw.e_cond.dtype)
         custom_fix = x0 and self.correcting_x0_fn is not None and not self._dynamic_thresholding
         if not self._needs_conversion(raw, sd, x0):
-            m_new = raw.e_cond if raw.e_cond.is_contiguous() else raw.e_cond.contiguous()
+            m_new = raw.e_cond if ops.CudaBackend._layout(raw.e_cond) is not None else raw.e_cond.contiguous()
             x_next = self._pure_update(co, x, m_new, m1, m2) if co is not None else None
             return m_new, x_next
         a = self._conv_args(raw, xe, alsig, sd, x0)
@@ -387,7 +392,7 @@ class DPM_Solver:
     def _state_like(t, sd):
         if t.dtype != sd:
             t = t.to(sd)
-        return t if t.is_contiguous() else t.contiguous()
+        return t if ops.CudaBackend._layout(t) is not None else t.contiguous()   # dense (row-major / channels_last)
 
     @staticmethod
     def _fill_update(a: StepArgs, co: P.Coeffs, x, m1, m2) -> None:

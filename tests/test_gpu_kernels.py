@@ -367,3 +367,35 @@ def test_second_output_copy(cuda_backend, sdt):
             cuda_backend.set_tuning(2, 0, 0)
             assert o.data_ptr() == buf.data_ptr()
             assert torch.equal(buf[:n].cpu(), ref_o) and torch.equal(buf[n:2 * n].cpu(), ref_o) and torch.equal(m.cpu(), ref_m)
+
+
+def test_channels_last_layout_is_kept(cuda_backend):
+    """Dense channels_last operands are used in place (no NCHW copy) and the outputs keep the layout."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    mk = lambda: torch.randn(6, 4, 32, 32, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    x, ec, eu, m1 = mk(), mk(), mk(), mk()
+    a = StepArgs(form=FORM_DIFF2, n_model=2, x=x, xe=x, e_cond=ec, e_uncond=eu, m1=m1, predict_x0=True, guidance=7.5,
+                 alpha_e=0.8, sigma_e=0.6, want_m_out=True, **coeffs(FORM_DIFF2, 3))
+    before = cuda_backend.launch_count()
+    m, o = cuda_backend.step(a)
+    assert cuda_backend.launch_count() - before == 1
+    assert m.is_contiguous(memory_format=torch.channels_last) and o.is_contiguous(memory_format=torch.channels_last)
+    ref_m, ref_o = OracleBackend().step(StepArgs(**{**a.__dict__, "x": x.cpu(), "xe": x.cpu(), "e_cond": ec.cpu(), "e_uncond": eu.cpu(), "m1": m1.cpu()}))
+    assert torch.equal(m.cpu(), ref_m) and torch.equal(o.cpu(), ref_o)
+    # mixed layouts still give the right values (inputs are brought to one layout)
+    a.m1 = m1.contiguous()
+    m2, o2 = cuda_backend.step(a)
+    assert torch.equal(o2, o) and torch.equal(m2, m)
+
+
+def test_sample_with_channels_last_network(golden, cuda_backend):
+    from cases import exact_net, seeded
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    from helpers import product_schedule
+    ns = product_schedule("sd")
+    net = lambda xx, tt: exact_net(xx, tt).contiguous(memory_format=torch.channels_last)
+    s = DPM_Solver(model_wrapper(net, ns), ns)
+    x = seeded((2, 4, 16, 16), 1234).cuda().contiguous(memory_format=torch.channels_last)
+    y = s.sample(x, steps=20, order=2)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    np.testing.assert_array_equal(y.cpu().numpy(), golden["samples"]["pp2m/y"])
