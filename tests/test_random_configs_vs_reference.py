@@ -92,3 +92,32 @@ def test_random_configurations_bit_exact(oracle_backend, chunk):
         for a, b in zip(in_, ir):
             np.testing.assert_array_equal(a.numpy(), b.numpy(), err_msg=str(c))
         done += 1
+
+
+@pytest.mark.parametrize("model_type", ["noise", "v", "x_start", "score"])
+def test_classifier_guidance_matches_reference(oracle_backend, model_type):
+    """guidance_type='classifier' (:315-321): eps - s*sigma_t*grad_x log p(c|x); the guided-diffusion
+    example drives the solver this way (runners/diffusion.py:611-628)."""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    kind, betas = make_betas("ddpm_linear")
+    W = torch.randn(5, 3 * 8 * 8, generator=torch.Generator().manual_seed(0)) * 0.05
+
+    def classifier_fn(x, t_in, cond, **kw):
+        logits = x.reshape(x.shape[0], -1) @ W.t() + 0.001 * t_in.reshape(-1, 1)
+        lp = torch.log_softmax(logits, dim=-1)
+        return lp[range(x.shape[0]), cond]
+
+    cond = torch.tensor([1, 3])
+    x = seeded((2, 3, 8, 8), 11)
+    outs = []
+    for mod in (ref, new):
+        ns = mod.NoiseScheduleVP("discrete", betas=torch.from_numpy(betas))
+        fn = mod.model_wrapper(exact_net, ns, model_type=model_type, guidance_type="classifier", condition=cond,
+                               guidance_scale=2.5, classifier_fn=classifier_fn)
+        eps = fn(x, torch.full((2,), 0.6))
+        s = mod.DPM_Solver(fn, ns, algorithm_type="dpmsolver++", correcting_x0_fn="dynamic_thresholding")
+        y = s.sample(x, steps=8, order=2)
+        outs.append((eps, y))
+    np.testing.assert_array_equal(outs[1][0].numpy(), outs[0][0].numpy())
+    np.testing.assert_array_equal(outs[1][1].numpy(), outs[0][1].numpy())
