@@ -15,10 +15,10 @@
 //     k_q_count  : the heavy pass, full occupancy, one read of the inputs at HBM rate: counts keys
 //                  below the bracket and compacts the ~2 % of keys inside it into the workspace
 //                  (block-local list, one global atomic pair per CTA).
-//     finish     : the LAST count-CTA of each sample (ticket counter) proves with the exact counts
-//                  whether both target ranks lie inside the bracket; if so an 11/11/10-bit radix
-//                  select over the candidates finishes, else (ties, adversarial data, mid-range q)
-//                  it runs the radix select over the whole sample from global memory. Always exact.
+//     k_q_finish : one CTA per sample; the exact counts prove whether both target ranks lie inside
+//                  the bracket; if so an 11/11/10-bit radix select over the candidates finishes,
+//                  else (ties, adversarial data, mid-range q) the CTA runs the radix select over
+//                  the whole sample from global memory. Always exact.
 //  B. cluster kernel (no workspace, small samples): one thread-block cluster per sample, keys parked
 //     in shared memory, per-digit histograms merged with distributed-shared-memory atomics.
 #include <cooperative_groups.h>
@@ -53,7 +53,7 @@ struct QParams {
   uint32_t iters;     // count kernel: consecutive chunks per CTA
 };
 // header words per sample
-enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_DONE = 7, H_WORDS = 8 };
+enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_WORDS = 8 };
 
 struct Sel {
   uint32_t bin, cnt;
@@ -169,7 +169,6 @@ __global__ void __launch_bounds__(kPThreads) k_q_pivots(const __grid_constant__ 
     h[H_HI] = hi_i >= kSamples ? 0xffffffffu : samp[hi_i];
     h[H_LT] = 0u;
     h[H_IN] = 0u;
-    h[H_DONE] = 0u;
     // The same two thresholds in "numerator space". x0 = RN(num / alpha) with num = xe - sigma*eps
     // is a monotone non-decreasing function of |num|, so
     //   key(x0) <  lo  <=>  |num| <  A_lo,   A_lo = min{a : RN(a/alpha) >= float(lo)}
@@ -199,72 +198,12 @@ __global__ void __launch_bounds__(kPThreads) k_q_pivots(const __grid_constant__ 
   }
 }
 
-// Exact finish of one sample, executed by the LAST count-CTA of that sample (ticket in the header):
-// with the exact counts in hand it proves whether both target ranks lie inside the bracket and runs an
-// 11/11/10-bit radix select over the candidates (read from the workspace, L2-resident), or over the
-// whole sample recomputed from global memory when they do not. `hist` is 8 KB of shared memory.
-template <int NE>
-__device__ __noinline__ void finish_sample(const KParams& p, const QParams& qp, uint64_t sample, uint32_t* hist,
-                                              uint32_t* ctrl) {
-  uint32_t* warp_sums = ctrl;
-  uint32_t* min_slot = ctrl + 16;
-  Sel* sel = reinterpret_cast<Sel*>(ctrl + 20);
-  const int tid = threadIdx.x;
-  uint32_t* hdr = qp.work + sample * H_WORDS;
-  const uint64_t C_lt = __ldcg(hdr + H_LT), C_in = __ldcg(hdr + H_IN);
-  const bool bracket_ok = C_in <= qp.cap && qp.lo >= C_lt && (qp.lo + qp.two) < C_lt + C_in;
-  if (tid == 0) {
-    *min_slot = 0xffffffffu;
-    hdr[H_PATH] = bracket_ok ? 1u : 2u;   // diagnostics: which path finished this sample
-  }
-  const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;
-  const size_t s_begin = sample * p.per_sample;
-  const uint64_t m = bracket_ok ? C_in : p.per_sample;             // keys the select runs over
-  uint64_t rank = bracket_ok ? qp.lo - C_lt : qp.lo;
-  auto key_at = [&](uint64_t i) -> uint32_t { return bracket_ok ? __ldcg(gc + i) : key_of_element<NE>(p, s_begin + i); };
-  __syncthreads();
-
-  uint32_t prefix = 0;
-  Sel sc;
-#pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    for (int i = tid; i < kBins; i += kPThreads) hist[i] = 0;
-    __syncthreads();
-    for (uint64_t i = tid; i < m; i += kPThreads) {
-      const uint32_t k = key_at(i);
-      if (pass == 0) atomicAdd(&hist[k >> 21], 1u);
-      else if (pass == 1) { if ((k >> 21) == prefix) atomicAdd(&hist[(k >> 10) & 2047u], 1u); }
-      else { if ((k >> 10) == prefix) atomicAdd(&hist[k & 1023u], 1u); }
-    }
-    __syncthreads();
-    sc = select_bin<kPThreads, kBins / kPThreads>(hist, rank, warp_sums, sel);
-    rank = sc.rank;
-    prefix = pass == 0 ? sc.bin : (pass == 1 ? ((prefix << 11) | sc.bin) : ((prefix << 10) | sc.bin));
-  }
-  const uint32_t key_lo = prefix;
-  uint32_t key_hi = key_lo;
-  if (qp.two && (sc.rank + 1 >= sc.cnt)) {                         // upper neighbour is the next larger key
-    uint32_t mn = 0xffffffffu;
-    for (uint64_t i = tid; i < m; i += kPThreads) {
-      const uint32_t k = key_at(i);
-      if (k > key_lo && k < mn) mn = k;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    if ((tid & 31) == 0 && mn != 0xffffffffu) atomicMin(min_slot, mn);
-    __syncthreads();
-    key_hi = *min_slot;
-  }
-  if (tid == 0) qp.s_out[sample] = finish_value(key_lo, key_hi, qp);
-}
-
 template <typename TE, typename TS, int NE, bool VEC, int U>
 __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ KParams p,
                                                         const __grid_constant__ QParams qp) {
   constexpr int kChunk = U * kPacket * kPThreads;
-  __shared__ uint32_t lcand[kLocalCand];   // bracket keys of this CTA; reused as the histogram by the last CTA
-  __shared__ uint32_t ctrl[32];
-  __shared__ uint32_t s_n, s_lt, s_base, s_last;
+  __shared__ uint32_t lcand[kLocalCand];
+  __shared__ uint32_t s_n, s_lt, s_base;
   const uint32_t cps = qp.slice;                                   // CTAs per sample
   const uint64_t sample = blockIdx.x / cps;
   const uint32_t part = blockIdx.x % cps;
@@ -392,16 +331,75 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
   } else if (n_local > kLocalCand && tid == 0) {
     atomicAdd(&hdr[H_IN], 0x40000000u);                            // poison: forces the exact fallback
   }
-  // ---- the last CTA of the sample finishes it (no third launch; overlaps with other samples' counting) ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&hdr[H_DONE], 1u) == cps - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    static_assert(kLocalCand >= kBins, "the candidate list doubles as the finish histogram");
-    finish_sample<NE>(p, qp, sample, lcand, ctrl);
+}
+
+template <int NE>
+__global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ KParams p,
+                                                         const __grid_constant__ QParams qp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);          // [kBins]
+  uint32_t* ctrl = hist + kBins;                                   // [32]
+  uint32_t* cand = ctrl + 32;                                      // [cap]
+  uint32_t* warp_sums = ctrl;
+  uint32_t* min_slot = ctrl + 16;
+  Sel* sel = reinterpret_cast<Sel*>(ctrl + 20);
+  const uint64_t sample = blockIdx.x;
+  const int tid = threadIdx.x;
+  uint32_t* hdr = qp.work + sample * H_WORDS;
+  const uint64_t C_lt = hdr[H_LT], C_in = hdr[H_IN];
+  const bool bracket_ok = C_in <= qp.cap && qp.lo >= C_lt && (qp.lo + qp.two) < C_lt + C_in;
+  if (tid == 0) {
+    *min_slot = 0xffffffffu;
+    hdr[H_PATH] = bracket_ok ? 1u : 2u;   // diagnostics: which path finished this sample
   }
+
+  uint64_t m;        // number of keys the select runs over
+  uint64_t rank;
+  const size_t s_begin = sample * p.per_sample;
+  if (bracket_ok) {
+    const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;
+    for (uint32_t i = tid; i < C_in; i += kPThreads) cand[i] = gc[i];
+    m = C_in;
+    rank = qp.lo - C_lt;
+  } else {
+    m = p.per_sample;                                              // exact fallback over the whole sample
+    rank = qp.lo;
+  }
+  auto key_at = [&](uint64_t i) -> uint32_t { return bracket_ok ? cand[i] : key_of_element<NE>(p, s_begin + i); };
+  __syncthreads();
+
+  uint32_t prefix = 0;
+  Sel sc;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = tid; i < kBins; i += kPThreads) hist[i] = 0;
+    __syncthreads();
+    for (uint64_t i = tid; i < m; i += kPThreads) {
+      const uint32_t k = key_at(i);
+      if (pass == 0) atomicAdd(&hist[k >> 21], 1u);
+      else if (pass == 1) { if ((k >> 21) == prefix) atomicAdd(&hist[(k >> 10) & 2047u], 1u); }
+      else { if ((k >> 10) == prefix) atomicAdd(&hist[k & 1023u], 1u); }
+    }
+    __syncthreads();
+    sc = select_bin<kPThreads, kBins / kPThreads>(hist, rank, warp_sums, sel);
+    rank = sc.rank;
+    prefix = pass == 0 ? sc.bin : (pass == 1 ? ((prefix << 11) | sc.bin) : ((prefix << 10) | sc.bin));
+  }
+  const uint32_t key_lo = prefix;
+  uint32_t key_hi = key_lo;
+  if (qp.two && (sc.rank + 1 >= sc.cnt)) {                         // upper neighbour is the next larger key
+    uint32_t mn = 0xffffffffu;
+    for (uint64_t i = tid; i < m; i += kPThreads) {
+      const uint32_t k = key_at(i);
+      if (k > key_lo && k < mn) mn = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((tid & 31) == 0 && mn != 0xffffffffu) atomicMin(min_slot, mn);
+    __syncthreads();
+    key_hi = *min_slot;
+  }
+  if (tid == 0) qp.s_out[sample] = finish_value(key_lo, key_hi, qp);
 }
 
 // =================================== B. cluster kernel ==========================================
@@ -583,7 +581,7 @@ static uint32_t pipeline_cap(uint64_t ps) {
   // the bracket itself is a random variable (its lower pivot is an order statistic of the sample):
   // measured on N(0,1) data at q = 0.995 it holds 1.2 - 5.2 % of the keys; 6.25 % + 2048 leaves > 4 sigma
   uint64_t cap = ps / 16 + 2048;
-  if (cap > (1u << 20)) cap = 1u << 20;
+  if (cap > 49152) cap = 49152;   // finish kernel keeps the candidates in shared memory
   return (uint32_t)cap;
 }
 
@@ -644,8 +642,14 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     qp.work = static_cast<uint32_t*>(workspace);
     if (n_samples * qp.slice > 0x7fffffffull) { set_error("too many chunks"); return DPM_ERR_UNSUPPORTED; }
     QKernel kp = p.n_model == 2 ? k_q_pivots<2> : k_q_pivots<1>;
+    QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
     kp<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
     kn<<<(unsigned)(n_samples * qp.slice), kPThreads, 0, stream>>>(p, qp);
+    const size_t fsmem = (size_t)(kBins + 32 + qp.cap) * sizeof(uint32_t);
+    int rc = ensure_max_smem(reinterpret_cast<const void*>(kf));
+    if (rc != 0) return rc;
+    kf<<<(unsigned)n_samples, kPThreads, fsmem, stream>>>(p, qp);
+    count_launch();
     count_launch();
     count_launch();
     return DPM_OK;
