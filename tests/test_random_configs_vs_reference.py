@@ -121,3 +121,41 @@ def test_classifier_guidance_matches_reference(oracle_backend, model_type):
         outs.append((eps, y))
     np.testing.assert_array_equal(outs[1][0].numpy(), outs[0][0].numpy())
     np.testing.assert_array_equal(outs[1][1].numpy(), outs[0][1].numpy())
+
+
+@pytest.mark.parametrize("method,order,steps", [("multistep", 2, 12), ("multistep", 3, 9), ("singlestep", 3, 10), ("singlestep_fixed", 2, 8)])
+@pytest.mark.parametrize("cfg", [None, 4.0])
+def test_hooks_match_reference(oracle_backend, method, order, steps, cfg):
+    """correcting_xt_fn (DiffEdit-style inpainting mask, :1180-1239) and a user correcting_x0_fn
+    (:440-441) see the same arguments in the same order and produce bit-identical samples."""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    kind, betas = make_betas("sd")
+    B = 2
+    x = seeded((B, 3, 8, 8), 31)
+    mask = (seeded((B, 3, 8, 8), 32) > 0).float()
+    known = seeded((B, 3, 8, 8), 33)
+    outs = []
+    for mod in (ref, new):
+        ns = mod.NoiseScheduleVP("discrete", betas=torch.from_numpy(betas))
+        log = []
+
+        def fix_xt(xt, t, step, _ns=ns, _log=log):
+            _log.append((round(float(t), 6), int(step)))
+            a, s = _ns.marginal_alpha(t.reshape(-1)[:1]), _ns.marginal_std(t.reshape(-1)[:1])
+            return xt * mask + (1 - mask) * (a * known + s * 0.5)
+
+        fix_x0 = lambda x0, t: torch.tanh(x0)
+        if cfg is not None:
+            net = lambda xx, tt, cc: exact_net(xx, tt) + 0.05 * cc.reshape(-1, 1, 1, 1)
+            fn = mod.model_wrapper(net, ns, guidance_type="classifier-free", condition=torch.ones(B, 1),
+                                   unconditional_condition=torch.zeros(B, 1), guidance_scale=cfg)
+        else:
+            fn = mod.model_wrapper(exact_net, ns)
+        s = mod.DPM_Solver(fn, ns, algorithm_type="dpmsolver++", correcting_x0_fn=fix_x0, correcting_xt_fn=fix_xt)
+        y, inter = s.sample(x, steps=steps, order=order, method=method, return_intermediate=True, denoise_to_zero=True)
+        outs.append((y, inter, log))
+    assert outs[0][2] == outs[1][2]
+    np.testing.assert_array_equal(outs[1][0].numpy(), outs[0][0].numpy())
+    for a, b in zip(outs[1][1], outs[0][1]):
+        np.testing.assert_array_equal(a.numpy(), b.numpy())
