@@ -223,6 +223,46 @@ def cpu_arm(w, sample_batch, repeats=1, warmup=0):
     return E * n_updates(w) / dt / 1e9, dt, cores
 
 
+def eager_cuda_arm(w, dev, repeats=3):
+    """The reference algorithm as stock eager PyTorch CUDA ops on the same GPU (oracle, torch namespace
+    on the device): per update 3/7/16 full-tensor launches plus ~40 tiny launches per schedule scalar.
+    fp32 state (the reference promotes every update to fp32). Returns (GElem/s, ms per sample())."""
+    from cases import make_betas
+    from oracle import dpm_oracle as O
+    TH = O.torch_namespace(dev)
+    kind, betas = make_betas(w["schedule"])
+    ns = O.VPSchedule.from_betas(betas, xp=TH) if kind == "discrete" else O.VPSchedule("linear", xp=TH)
+    shape = tuple(w["shape"])
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(shape, device=dev, generator=g)
+    nb = 2 if w["cfg"] else 1
+    banks = [torch.randn((nb * shape[0],) + shape[1:], device=dev, generator=g) for _ in range(2)]
+    cnt = [0]
+
+    def net(xx, tt):
+        cnt[0] += 1
+        return banks[cnt[0] % 2]
+
+    smp = O.Sampler(ns, net, algorithm_type=w["algo"], guidance_scale=w["cfg"],
+                    thresholding=(0.995, 1.0) if w["thresholding"] else None)
+    smp.log_calls = False
+    if w["thresholding"]:
+        return None   # the oracle's quantile is a numpy sort: not an eager-CUDA path
+    once = (lambda: smp.multistep(x, w["steps"], w["order"])) if w["method"] == "multistep" else \
+        (lambda: smp.singlestep(x, w["steps"], w["order"]))
+    with torch.no_grad():
+        once()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            once()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / repeats
+    return int(np.prod(shape)) * n_updates(w) / (ms * 1e-3) / 1e9, ms
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -511,6 +551,13 @@ def run_b200(args, w):
             val, dtc, cores = cpu_arm(w, sample_batch, repeats=1, warmup=1)
             out["cpu_baseline"] = {"value": val, "unit": "GElem/s", "cores": cores, "kind": "port",
                                    "sample": f"[{sample_batch},{','.join(map(str, shape[1:]))}] fp32, {w['steps']} solver steps, {dtc * 1e3:.0f} ms"}
+            try:
+                eg = eager_cuda_arm(w, dev)
+                if eg is not None:
+                    out["eager_cuda_baseline"] = {"value": eg[0], "unit": "GElem/s", "ms_per_step": eg[1], "dtype": "f32",
+                                                  "what": "the reference algorithm as stock eager PyTorch CUDA kernels on the same GPU (oracle port, torch namespace on cuda), full workload shape"}
+            except Exception as e:   # never let the extra leg break the bench line
+                out["eager_cuda_baseline"] = {"error": repr(e)[:200]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

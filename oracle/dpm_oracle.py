@@ -86,7 +86,7 @@ class _NP:
 NP = _NP()
 
 
-def _torch_ns():
+def _torch_ns(device="cpu"):
     import torch
 
     class _TH:
@@ -95,7 +95,7 @@ def _torch_ns():
 
         @staticmethod
         def asarray(v, dtype=torch.float32):
-            return torch.as_tensor(v, dtype=dtype)
+            return torch.as_tensor(v, dtype=dtype, device=device)
 
         exp, log, sqrt, expm1 = torch.exp, torch.log, torch.sqrt, torch.expm1
         logaddexp, abs, maximum = torch.logaddexp, torch.abs, torch.maximum
@@ -106,7 +106,7 @@ def _torch_ns():
 
         @staticmethod
         def linspace(a, b, n):
-            return torch.linspace(a, b, n)
+            return torch.linspace(a, b, n).to(device)     # the reference builds grids on CPU, then .to(device) (:474)
 
         @staticmethod
         def cat(xs):
@@ -122,7 +122,7 @@ def _torch_ns():
 
         @staticmethod
         def zeros1():
-            return torch.zeros((1,))
+            return torch.zeros((1,), device=device)
 
         @staticmethod
         def reshape(a, shape):
@@ -131,8 +131,10 @@ def _torch_ns():
     return _TH()
 
 
-def torch_namespace():
-    return _torch_ns()
+def torch_namespace(device="cpu"):
+    """torch ops on `device`: 'cpu' = the CPU baseline; 'cuda' = the reference algorithm as stock eager
+    PyTorch CUDA kernels (every scalar op a launch, every update 3/7/16 full-tensor launches)."""
+    return _torch_ns(device)
 
 
 def _scalar(xp, v):
@@ -145,12 +147,36 @@ def _scalar(xp, v):
 # ---------------------------------------------------------------------------------------------
 # NoiseScheduleVP (reference :6-167) and interpolate_fn (:1253-1292)
 # ---------------------------------------------------------------------------------------------
+def _interpolate_tensor_ops(x, kx, ky):
+    """torch namespace: interpolate_fn as a chain of tensor ops without host control flow, the way the
+    reference runs it on a device (cat, sort, argmin, where, gather :1266-1291) -- one launch per op."""
+    import torch
+    n, K = x.shape[0], kx.shape[0]
+    both = torch.cat([x.reshape(n, 1), kx.reshape(1, K).repeat(n, 1)], dim=1)      # :1267
+    srt, order = torch.sort(both, dim=1)                                             # :1268
+    pos = torch.argmin(order, dim=1)                                                 # :1269
+    below = pos - 1
+    one = torch.tensor(1, device=x.device)
+    last = torch.tensor(K - 2, device=x.device)
+    start = torch.where(torch.eq(pos, 0), one, torch.where(torch.eq(pos, K), last, below))        # :1271-1277
+    end = torch.where(torch.eq(start, below), start + 2, start + 1)                               # :1278
+    x0 = torch.gather(srt, 1, start.unsqueeze(1)).squeeze(1)                                     # :1279
+    x1 = torch.gather(srt, 1, end.unsqueeze(1)).squeeze(1)                                       # :1280
+    s2 = torch.where(torch.eq(pos, 0), torch.tensor(0, device=x.device), torch.where(torch.eq(pos, K), last, below))  # :1281-1287
+    kyb = ky.reshape(1, K).expand(n, -1)                                                          # :1288
+    y0 = torch.gather(kyb, 1, s2.unsqueeze(1)).squeeze(1)                                        # :1289
+    y1 = torch.gather(kyb, 1, (s2 + 1).unsqueeze(1)).squeeze(1)                                  # :1290
+    return y0 + (x - x0) * (y1 - y0) / (x1 - x0)                                                 # :1291
+
+
 def interpolate(xp, x, kx, ky):
     """Piecewise-linear f(x) through keypoints (kx, ky), linear extrapolation outside.
 
     Follows interpolate_fn :1266-1291 literally, one query at a time: sort the query together with
     the keypoints (query first), locate it, pick the bracketing keypoints, then
     y0 + (x - x0) * (y1 - y0) / (x1 - x0)."""
+    if xp.name == "torch":
+        return _interpolate_tensor_ops(x, kx, ky)
     K = kx.shape[0]
     out = []
     for q in range(x.shape[0]):
@@ -498,6 +524,7 @@ class Sampler:
         self.ns, self.net, self.algo = ns, net, algorithm_type
         self.model_type, self.scale, self.thr = model_type, guidance_scale, thresholding
         self.calls = []   # (t_in[0], x.shape) per network call
+        self.log_calls = True   # reading t_in[0] syncs a device; timing runs switch it off
 
     def noise(self, x, t):                              # model_fn :309-330 + self.model :404
         xp = self.ns.xp
@@ -505,11 +532,13 @@ class Sampler:
         t1 = _scalar(xp, t)[0:1]                        # one time label for the whole batch (:404)
         if self.scale is None:
             t_in = model_input_time(self.ns, xp.cat([t1] * B))
-            self.calls.append((float(t_in[0]), tuple(x.shape)))
+            if self.log_calls:
+                self.calls.append((float(t_in[0]), tuple(x.shape)))
             return to_noise(self.ns, self.model_type, x, self.net(x, t_in), t1)
         x2 = xp.cat([x, x])                             # :326
         t_in = model_input_time(self.ns, xp.cat([t1] * (2 * B)))   # :327
-        self.calls.append((float(t_in[0]), tuple(x2.shape)))
+        if self.log_calls:
+            self.calls.append((float(t_in[0]), tuple(x2.shape)))
         both = to_noise(self.ns, self.model_type, x2, self.net(x2, t_in), t1)
         return cfg_combine(both[:B], both[B:], self.scale)          # :329-330, uncond half first
 
