@@ -348,7 +348,7 @@ def make_timed_backend():
     return TimedBackend()
 
 
-def headline_kernels(be, peak, shape=(4096, 4, 64, 64), reps=30):
+def headline_kernels(be, peak, shape=(4096, 4, 64, 64), reps=50):
     """North-star kernel timed alone: fused 3rd-order multistep update, x + 3 buffers -> x_t."""
     from dpm_solver_b200.ops import StepArgs, FORM_MS3
     out = {}
@@ -361,7 +361,7 @@ def headline_kernels(be, peak, shape=(4096, 4, 64, 64), reps=30):
             x, m0, m1, m2, o = sets[i % 3]
             be.step(StepArgs(form=FORM_MS3, x=x, m0=m0, m1=m1, m2=m2, out=o, a=0.95, c0=-0.1, c1=0.05, c2=-0.01,
                              w0=1.02, w1=0.98, w2=0.51, w3=0.5))
-        for i in range(5):
+        for i in range(10):
             launch(i)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
