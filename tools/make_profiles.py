@@ -89,6 +89,11 @@ def main():
         cb = benches["c2"].get("cpu_baseline")
         if cb:
             md += ["", f"CPU baseline beside it (same job, rank 0): {cb['value']:.3f} GElem/s, {cb['cores']} threads, {cb['sample']}."]
+        eg = benches["c2"].get("eager_cuda_baseline")
+        if eg and "value" in eg:
+            md += ["", f"Second baseline, same GPU: the reference algorithm as stock eager PyTorch CUDA kernels (oracle port, torch namespace on "
+                   f"cuda, fp32 state, full C2 shape): **{eg['value']:.1f} GElem/s** ({eg['ms_per_step']:.1f} ms per 20-step sample()) — "
+                   f"{benches['c2']['value'] / eg['value']:.0f}x below the fused bf16 path ({benches['c2']['value']:.0f} GElem/s)."]
     md.append("")
     # ---- per-kernel event table + ncu launch share ----
     for w, d in benches.items():
