@@ -150,6 +150,9 @@ def main():
         p = os.path.join(SRC, extra)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(DST, f"{R}_{extra}"))
+    appendix = os.path.join(DST, f"{R}_appendix.md")
+    if os.path.exists(appendix):
+        md.append(open(appendix).read().rstrip())
     open(os.path.join(DST, "README.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md)[:3000])
 
