@@ -36,7 +36,6 @@ constexpr int kQThreads = 512;      // cluster kernel
 constexpr int kBins = 2048;
 constexpr int kSamples = 1024;      // sample keys per sample (pivot kernel)
 constexpr int kPThreads = 256;      // pivot / count / finish kernels
-constexpr int kChunkMax = 8192;     // elements per CTA iteration of the count kernel (U = 4 packets per thread)
 constexpr int kLocalCand = 2048;    // bracket keys one count-CTA may collect
 
 struct QParams {
