@@ -148,24 +148,43 @@ __global__ void __launch_bounds__(kPThreads) k_q_pivots(const __grid_constant__ 
     samp[j] = key_of_element<NE>(p, s_begin + pos);
   }
   __syncthreads();
-  for (int k = 2; k <= kSamples; k <<= 1) {       // bitonic sort, ascending
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  // only two order statistics of the sample are needed: 11/11/10-bit radix select in shared memory
+  // (a full bitonic sort of the 1024 keys cost 10x the instructions and made this kernel issue-bound)
+  __shared__ uint32_t hist[kBins];
+  __shared__ __align__(16) uint32_t ctrl[32];
+  __shared__ uint32_t s_piv[2];
+  const int64_t ps_rank = (int64_t)(((unsigned __int128)qp.lo * kSamples) / p.per_sample);
+  const int64_t want[2] = {ps_rank - qp.margin, ps_rank + qp.margin + 1};
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    if (want[which] < 0 || want[which] >= kSamples) {
+      if (threadIdx.x == 0) s_piv[which] = which == 0 ? 0u : 0xffffffffu;
+      continue;
+    }
+    uint64_t rank = (uint64_t)want[which];
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+      for (int i = threadIdx.x; i < kBins; i += kPThreads) hist[i] = 0;
+      __syncthreads();
       for (int i = threadIdx.x; i < kSamples; i += kPThreads) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint32_t x = samp[i], y = samp[l];
-          if ((x > y) == ((i & k) == 0)) { samp[i] = y; samp[l] = x; }
-        }
+        const uint32_t k = samp[i];
+        if (pass == 0) atomicAdd(&hist[k >> 21], 1u);
+        else if (pass == 1) { if ((k >> 21) == prefix) atomicAdd(&hist[(k >> 10) & 2047u], 1u); }
+        else { if ((k >> 10) == prefix) atomicAdd(&hist[k & 1023u], 1u); }
       }
       __syncthreads();
+      const Sel sc = select_bin<kPThreads, kBins / kPThreads>(hist, rank, ctrl, reinterpret_cast<Sel*>(ctrl + 20));
+      rank = sc.rank;
+      prefix = pass == 0 ? sc.bin : (pass == 1 ? ((prefix << 11) | sc.bin) : ((prefix << 10) | sc.bin));
     }
+    if (threadIdx.x == 0) s_piv[which] = prefix;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const int64_t ps = (int64_t)(((unsigned __int128)qp.lo * kSamples) / p.per_sample);
-    const int64_t lo_i = ps - qp.margin, hi_i = ps + qp.margin + 1;
     uint32_t* h = qp.work + sample * H_WORDS;
-    h[H_LO] = lo_i < 0 ? 0u : samp[lo_i];
-    h[H_HI] = hi_i >= kSamples ? 0xffffffffu : samp[hi_i];
+    h[H_LO] = s_piv[0];
+    h[H_HI] = s_piv[1];
     h[H_LT] = 0u;
     h[H_IN] = 0u;
     // The same two thresholds in "numerator space". x0 = RN(num / alpha) with num = xe - sigma*eps
@@ -335,10 +354,8 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
 template <int NE>
 __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ KParams p,
                                                          const __grid_constant__ QParams qp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);          // [kBins]
-  uint32_t* ctrl = hist + kBins;                                   // [32]
-  uint32_t* cand = ctrl + 32;                                      // [cap]
+  __shared__ uint32_t hist[kBins];
+  __shared__ __align__(16) uint32_t ctrl[32];
   uint32_t* warp_sums = ctrl;
   uint32_t* min_slot = ctrl + 16;
   Sel* sel = reinterpret_cast<Sel*>(ctrl + 20);
@@ -355,16 +372,15 @@ __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ 
   uint64_t m;        // number of keys the select runs over
   uint64_t rank;
   const size_t s_begin = sample * p.per_sample;
+  const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;   // candidates: L2-resident
   if (bracket_ok) {
-    const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;
-    for (uint32_t i = tid; i < C_in; i += kPThreads) cand[i] = gc[i];
     m = C_in;
     rank = qp.lo - C_lt;
   } else {
     m = p.per_sample;                                              // exact fallback over the whole sample
     rank = qp.lo;
   }
-  auto key_at = [&](uint64_t i) -> uint32_t { return bracket_ok ? cand[i] : key_of_element<NE>(p, s_begin + i); };
+  auto key_at = [&](uint64_t i) -> uint32_t { return bracket_ok ? __ldcg(gc + i) : key_of_element<NE>(p, s_begin + i); };
   __syncthreads();
 
   uint32_t prefix = 0;
@@ -580,7 +596,7 @@ static uint32_t pipeline_cap(uint64_t ps) {
   // the bracket itself is a random variable (its lower pivot is an order statistic of the sample):
   // measured on N(0,1) data at q = 0.995 it holds 1.2 - 5.2 % of the keys; 6.25 % + 2048 leaves > 4 sigma
   uint64_t cap = ps / 16 + 2048;
-  if (cap > 49152) cap = 49152;   // finish kernel keeps the candidates in shared memory
+  if (cap > (1u << 20)) cap = 1u << 20;
   return (uint32_t)cap;
 }
 
@@ -644,10 +660,7 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
     kp<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
     kn<<<(unsigned)(n_samples * qp.slice), kPThreads, 0, stream>>>(p, qp);
-    const size_t fsmem = (size_t)(kBins + 32 + qp.cap) * sizeof(uint32_t);
-    int rc = ensure_max_smem(reinterpret_cast<const void*>(kf));
-    if (rc != 0) return rc;
-    kf<<<(unsigned)n_samples, kPThreads, fsmem, stream>>>(p, qp);
+    kf<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
     count_launch();
     count_launch();
     count_launch();
