@@ -162,8 +162,7 @@ class CudaBackend:
         d.guidance, d.alpha_e, d.sigma_e = a.guidance, a.alpha_e, a.sigma_e
         d.a, d.c0, d.c1, d.c2 = a.a, a.c0, a.c1, a.c2
         d.w0, d.w1, d.w2, d.w3, d.w4 = a.w0, a.w1, a.w2, a.w3, a.w4
-        self._last_layout = layout
-        return d, keep, ref, sdt
+        return d, keep, ref, sdt, layout
 
     def _new_like(self, ref, sdt, layout):
         if layout == "cl":
@@ -174,18 +173,18 @@ class CudaBackend:
     # -- API -----------------------------------------------------------------------------
     def step(self, a: StepArgs) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Launch one fused step. Returns (m_out, out); either may be None."""
-        d, keep, ref, sdt = self._fill(a)
+        d, keep, ref, sdt, layout = self._fill(a)
         m_out = out = None
         if a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE):
-            m_out = a.m_out if a.m_out is not None else self._new_like(ref, sdt, self._last_layout)
+            m_out = a.m_out if a.m_out is not None else self._new_like(ref, sdt, layout)
             self._check(m_out, "m_out", ref.device, ref.numel(), sdt)
-            if self._layout(m_out) != self._last_layout:
+            if self._layout(m_out) != layout:
                 raise ValueError("dpm_solver_b200: preallocated m_out must be dense and laid out like the inputs")
             d.m_out = m_out.data_ptr()
         if a.form != FORM_NONE:
-            out = a.out if a.out is not None else self._new_like(ref, sdt, self._last_layout)
+            out = a.out if a.out is not None else self._new_like(ref, sdt, layout)
             self._check(out, "out", ref.device, ref.numel(), sdt)
-            if self._layout(out) != self._last_layout:
+            if self._layout(out) != layout:
                 raise ValueError("dpm_solver_b200: preallocated out must be dense and laid out like the inputs")
             d.out = out.data_ptr()
             if a.out2 is not None:
@@ -211,7 +210,7 @@ class CudaBackend:
         """Per-sample s_b = max(quantile(|x0_b|, q), max_val) -> fp32 [B].
         return_stats=True also returns the pipeline's per-sample header words (int32 [B, 8]:
         lo key, hi key, #below, #inside, path (1 bracket / 2 exact fallback), ...) for diagnostics."""
-        d, keep, ref, _ = self._fill(a)
+        d, keep, ref, _, _ = self._fill(a)
         if a.per_sample <= 0 or ref.numel() % a.per_sample:
             raise ValueError("dpm_solver_b200: per_sample must divide numel")
         nb = ref.numel() // a.per_sample
