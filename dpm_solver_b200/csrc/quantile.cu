@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
 template <int NE>
 __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ KParams p,
                                                          const __grid_constant__ QParams qp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw);          // [cap]: candidates staged once (3 passes read them)
   __shared__ uint32_t hist[kBins];
   __shared__ __align__(16) uint32_t ctrl[32];
   uint32_t* warp_sums = ctrl;
@@ -372,15 +374,20 @@ __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ 
   uint64_t m;        // number of keys the select runs over
   uint64_t rank;
   const size_t s_begin = sample * p.per_sample;
-  const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;   // candidates: L2-resident
+  const uint32_t* gc = qp.work + qp.n_samples * H_WORDS + sample * (uint64_t)qp.cap;
+  const bool staged = bracket_ok && qp.slice != 0 && C_in <= qp.cap;   // qp.slice reused: 1 = shared-memory staging fits
   if (bracket_ok) {
+    if (staged)
+      for (uint32_t i = tid; i < C_in; i += kPThreads) cand[i] = gc[i];
     m = C_in;
     rank = qp.lo - C_lt;
   } else {
     m = p.per_sample;                                              // exact fallback over the whole sample
     rank = qp.lo;
   }
-  auto key_at = [&](uint64_t i) -> uint32_t { return bracket_ok ? __ldcg(gc + i) : key_of_element<NE>(p, s_begin + i); };
+  auto key_at = [&](uint64_t i) -> uint32_t {
+    return bracket_ok ? (staged ? cand[i] : __ldcg(gc + i)) : key_of_element<NE>(p, s_begin + i);
+  };
   __syncthreads();
 
   uint32_t prefix = 0;
@@ -660,7 +667,15 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
     kp<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
     kn<<<(unsigned)(n_samples * qp.slice), kPThreads, 0, stream>>>(p, qp);
-    kf<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
+    // finish: stage the candidates in shared memory when they fit next to 3 co-resident CTAs (else read L2)
+    QParams qf = qp;
+    const size_t fsmem = (size_t)qp.cap * sizeof(uint32_t);
+    qf.slice = fsmem <= 64 * 1024 ? 1u : 0u;
+    if (qf.slice) {
+      int rc = ensure_max_smem(reinterpret_cast<const void*>(kf));
+      if (rc != 0) return rc;
+    }
+    kf<<<(unsigned)n_samples, kPThreads, qf.slice ? fsmem : 0, stream>>>(p, qf);
     count_launch();
     count_launch();
     count_launch();
