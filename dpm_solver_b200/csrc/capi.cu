@@ -56,7 +56,10 @@ int ensure_max_smem(const void* kernel, bool nonportable_cluster) {
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
   if (done.count({dev, kernel})) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin());
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  const int room = max_smem_optin() - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 0);   // static smem counts too
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, room);
   if (e == cudaSuccess && nonportable_cluster)
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e != cudaSuccess) {
