@@ -11,12 +11,14 @@
 //   fence.proxy.async -> thread 0: bulk wait_group.read(S-2) (frees the out-buffers of the
 //   next stage) -> __syncthreads -> thread 0: bulk-store stage s, commit, then refill the
 //   input buffers of stage s with tile i+S.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.cuh"
 
 namespace dpm {
 
-constexpr int kTmaUnroll = 2;
+constexpr int kTmaUnits = 2;   // default packets per thread per tile (tile = threads * units packets)
 constexpr int kTmaMaxThreads = 512;
 constexpr int kMaxStages = 8;
 
@@ -81,14 +83,14 @@ struct StageLayout {
 template <typename TE, typename TS, int NE, int FORM>
 __global__ void __launch_bounds__(kTmaMaxThreads)
     k_step_tma(const __grid_constant__ KParams p, const __grid_constant__ StageLayout L,
-               const int stages) {
+               const int stages, const int units) {
   using Needs = FormNeeds<FORM>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kMaxStages]
   unsigned char* ring = smem + 128;
 
   const int tid = threadIdx.x;
-  const uint32_t tile_pk = blockDim.x * kTmaUnroll;
+  const uint32_t tile_pk = blockDim.x * units;
   const uint32_t tile_el = tile_pk * kPacket;
   const uint32_t ntiles = (p.npk + tile_pk - 1) / tile_pk;
   const bool has_x = Needs::kX || (NE > 0 && p.use_xe);  // state slot: x, or xe when no update
@@ -146,8 +148,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
 
     mbar_wait(&full[s], parity);
 
-#pragma unroll
-    for (int u = 0; u < kTmaUnroll; ++u) {
+#pragma unroll 2
+    for (int u = 0; u < units; ++u) {
       const uint32_t lp = u * blockDim.x + tid;  // packet inside the tile
       if (lp < pk_here) {
         const uint32_t le = lp * kPacket;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   if (tid == 0) bulk_wait_all();
 }
 
-typedef void (*TmaKernel)(const KParams, const StageLayout, const int);
+typedef void (*TmaKernel)(const KParams, const StageLayout, const int, const int);
 
 template <typename TE, typename TS, int NE>
 static TmaKernel tma_form(int form) {
@@ -261,20 +263,28 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const bool m2 = p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
   const int n_streams = (need_x || (p.n_model > 0 && p.use_xe)) + sep_xe + p.n_model + (p.n_model == 0) + m1 + m2 +
                         (p.n_model > 0 && p.m_out != nullptr) + need_x;
-  // 16-bit sweep (profiles/): <= 4 streams run best with 3 CTAs/SM (768 resident threads), more with 2
-  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : ((n_streams <= 4 && ss == 2) ? 3 : 2);
+  // 16-bit sweeps (profiles/r01_sweep2.jsonl, r01_tma_units.txt): <= 4 streams run best as 256 threads x 3
+  // CTAs/SM, 5-6 streams as 128 x 4 (smaller tiles, finer interleaving), 7+ as 256 x 2; two stages each
+  int def_threads = 256, def_ctas = 2;
+  if (ss == 2 && ms == 2) {
+    if (n_streams <= 4) { def_threads = 256; def_ctas = 3; }
+    else if (n_streams <= 6) { def_threads = 128; def_ctas = 4; }
+  }
+  const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : def_ctas;
   // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
   const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
   const size_t budget = per_cta < (size_t)max_smem_optin() ? per_cta : (size_t)max_smem_optin();
 
   StageLayout L;
   int threads = 0, stages = 0;
-  // tile = threads * kTmaUnroll packets. Default 256 threads x 2 CTAs/SM (512 resident threads):
+  int units = kTmaUnits;
+  if (const char* e = getenv("DPM_TMA_UNITS")) { const int v = atoi(e); if (v >= 1 && v <= 8) units = v; }
+  // tile = threads * units packets. Default 256 threads x 2 CTAs/SM (512 resident threads):
   // the sweep in profiles/ shows two stages at that size beat more, smaller stages; the tile only
   // shrinks when two stages of it do not fit.
-  const int cand[4] = {t.threads > 0 ? t.threads : 256, 128, 64, 32};
+  const int cand[4] = {t.threads > 0 ? t.threads : def_threads, 128, 64, 32};
   for (int c = 0; c < (t.threads > 0 ? 1 : 4); ++c) {
-    const uint32_t tile_el = (uint32_t)cand[c] * kTmaUnroll * kPacket;
+    const uint32_t tile_el = (uint32_t)cand[c] * units * kPacket;
     uint32_t o = 0;
     auto take = [&](bool on, uint32_t es) { uint32_t r = 0xffffffffu; if (on) { r = o; o += tile_el * es; } return r; };
     L.x = take(need_x || (p.n_model > 0 && p.use_xe), ss);
@@ -296,14 +306,14 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   if (stages < 2) return 1;
   const size_t smem = 128 + (size_t)stages * L.bytes;
 
-  const uint32_t tile_pk = (uint32_t)threads * kTmaUnroll;
+  const uint32_t tile_pk = (uint32_t)threads * units;
   const uint64_t ntiles = ((uint64_t)p.npk + tile_pk - 1) / tile_pk;
   const uint64_t cap = (uint64_t)sm_count() * ctas;
   const uint32_t grid = (uint32_t)(ntiles < cap ? ntiles : cap);
   if (grid == 0) return 0;
   int rc = ensure_max_smem(reinterpret_cast<const void*>(k));  // once per kernel and device
   if (rc != 0) return rc;
-  k<<<grid, threads, smem, stream>>>(p, L, stages);
+  k<<<grid, threads, smem, stream>>>(p, L, stages, units);
   count_launch();
   return 0;
 }
