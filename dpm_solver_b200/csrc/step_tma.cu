@@ -264,12 +264,11 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const int n_streams = (need_x || (p.n_model > 0 && p.use_xe)) + sep_xe + p.n_model + (p.n_model == 0) + m1 + m2 +
                         (p.n_model > 0 && p.m_out != nullptr) + need_x;
   // 16-bit sweeps (profiles/r01_sweep2.jsonl, r01_tma_units.txt): <= 4 streams run best as 256 threads x 3
-  // CTAs/SM, 5-6 streams as 128 x 4 (smaller tiles, finer interleaving), 7+ as 256 x 2; two stages each
+  // CTAs/SM, more as 256 x 2. 128 x 4 wins the isolated back-to-back sweep for 5-6 streams by ~3% but
+  // LOSES 4-7% inside the sampling loop (bench.py c2/c3, interleaved with the model's kernels), so the
+  // in-loop result decides.
   int def_threads = 256, def_ctas = 2;
-  if (ss == 2 && ms == 2) {
-    if (n_streams <= 4) { def_threads = 256; def_ctas = 3; }
-    else if (n_streams <= 6) { def_threads = 128; def_ctas = 4; }
-  }
+  if (ss == 2 && ms == 2 && n_streams <= 4) def_ctas = 3;
   const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : def_ctas;
   // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
   const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
