@@ -21,6 +21,7 @@ from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
+import torch.distributed as dist
 
 from . import ops, plan as P
 from ._lib import FORM_LIN1, FORM_NONE, FORM_SS3T, PARAM_BY_NAME, PARAM_NOISE
@@ -625,7 +626,13 @@ class DPM_Solver:
                                                times_dev=td)
             # E = max_b sqrt(mean(((x_higher - x_lower)/delta)^2)), delta = max(atol, rtol*max(|x_lower|,|x_prev|))
             # (:999-1001): one fused reduction launch; the accept/reject test needs E on the host (:1002)
-            E = ops.backend().error_norm(x_higher, x_lower, self._state_like(x_prev, x_higher.dtype), atol, rtol).cpu()
+            E = ops.backend().error_norm(x_higher, x_lower, self._state_like(x_prev, x_higher.dtype), atol, rtol)
+            if self.plan_broadcast and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # batch-sharded run: E is a max over the batch (:1001), so one 4-byte all-reduce(max) per
+                # iteration makes every rank take the single-process controller's decisions
+                E = E.reshape(1).float()
+                dist.all_reduce(E, op=dist.ReduceOp.MAX)
+            E = E.cpu()
             if torch.all(E <= 1.):
                 x = x_higher
                 s = t

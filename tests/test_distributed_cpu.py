@@ -37,6 +37,10 @@ def _worker(rank, world, port, outdir):
     s2 = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver", plan_broadcast=True)
     y2 = s2.sample(shard_batch(x).contiguous(), steps=9, order=3, method="singlestep")
     np.save(os.path.join(outdir, f"z{rank}.npy"), y2.numpy())
+    # adaptive: the error estimate is a max over the batch -> one all-reduce(max) per iteration
+    s3 = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver", plan_broadcast=True)
+    y3 = s3.sample(shard_batch(x).contiguous(), order=2, method="adaptive", atol=0.05, rtol=0.1)
+    np.save(os.path.join(outdir, f"a{rank}.npy"), y3.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,6 +61,10 @@ def test_two_rank_shards_equal_single_process(tmp_path, oracle_backend):
     np.testing.assert_array_equal(got, full)
     full = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver").sample(x, steps=9, order=3, method="singlestep").numpy()
     got = np.concatenate([np.load(tmp_path / "z0.npy"), np.load(tmp_path / "z1.npy")])
+    np.testing.assert_array_equal(got, full)
+    full = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver").sample(
+        x, order=2, method="adaptive", atol=0.05, rtol=0.1).numpy()
+    got = np.concatenate([np.load(tmp_path / "a0.npy"), np.load(tmp_path / "a1.npy")])
     np.testing.assert_array_equal(got, full)
 
 

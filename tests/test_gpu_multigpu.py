@@ -32,6 +32,10 @@ def _worker(rank, world, port, outdir):
     y2 = s.sample(xs, steps=10, order=3)          # second call: cached plan, no collective
     assert torch.equal(y, y2)
     np.save(os.path.join(outdir, f"y{rank}.npy"), y.cpu().numpy())
+    # adaptive: E is a batch max -> one 4-byte all-reduce(max) per iteration keeps the ranks in lock step
+    sa = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver", plan_broadcast=True)
+    ya = sa.sample(xs, order=2, method="adaptive", atol=0.05, rtol=0.1)
+    np.save(os.path.join(outdir, f"a{rank}.npy"), ya.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,4 +53,8 @@ def test_nccl_shards_equal_single_gpu(tmp_path, cuda_backend):
     x = seeded((12, 3, 32, 32), 5).cuda()
     full = DPM_Solver(model_wrapper(exact_net, ns), ns, correcting_x0_fn="dynamic_thresholding").sample(x, steps=10, order=3)
     got = np.concatenate([np.load(tmp_path / f"y{r}.npy") for r in range(world)])
+    np.testing.assert_array_equal(got, full.cpu().numpy())
+    full = DPM_Solver(model_wrapper(exact_net, ns), ns, algorithm_type="dpmsolver").sample(
+        x, order=2, method="adaptive", atol=0.05, rtol=0.1)
+    got = np.concatenate([np.load(tmp_path / f"a{r}.npy") for r in range(world)])
     np.testing.assert_array_equal(got, full.cpu().numpy())
