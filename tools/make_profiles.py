@@ -121,7 +121,15 @@ def main():
     json.dump(traffic, open(os.path.join(DST, "roofline_traffic.json"), "w"), indent=1)
     # ---- ncu full ----
     reps = sorted(f for f in os.listdir(SRC) if f.endswith(".ncu-rep"))
-    if reps:
+    pre = os.path.join(SRC, "ncu_summary.md")
+    if os.path.exists(pre) and os.path.exists(os.path.join(SRC, "ncu_summary.json")):
+        # tools/gpu_round_final.sh summarised the captures on the GPU box (the .ncu-rep files stay there)
+        shutil.copy(pre, os.path.join(DST, f"{R}_ncu_summary.md"))
+        shutil.copy(os.path.join(SRC, "ncu_summary.json"), os.path.join(DST, f"{R}_ncu_summary.json"))
+        md += ["## `ncu --set full` captures (one launch each, `--clock-control none`)", "", open(pre).read().strip(), "",
+               f"Full metric dump: `profiles/{R}_ncu_summary.json` (incl. stall reasons and SASS mnemonic counts: `UBLKCP` = TMA bulk copy, "
+               "`SYNCS` = mbarrier, `LDG.E…256/128` vector loads, `UCGABAR` = cluster barrier).", ""]
+    elif reps:
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py")] + [os.path.join(SRC, f) for f in reps] +
                              ["--out", os.path.join(DST, f"{R}_ncu_summary")], capture_output=True, text=True).stdout
         md += ["## `ncu --set full` captures (one launch each, `--clock-control none`)", "", out.strip(), "",
