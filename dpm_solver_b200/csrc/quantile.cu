@@ -50,6 +50,7 @@ struct QParams {
   uint32_t* work;     // pipeline workspace: [n_samples][8] header words, then [n_samples][cap] candidates
   uint64_t n_samples;
   uint32_t iters;     // count kernel: consecutive chunks per CTA
+  uint32_t num_space; // pipeline: bracket keys are |numerator| patterns (plain eps -> x0 map, alpha > 0)
 };
 // header words per sample
 enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_WORDS = 8 };
@@ -228,33 +229,36 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
   uint32_t* hdr = qp.work + sample * H_WORDS;
   const uint32_t lo_k = hdr[H_LO], hi_k = hdr[H_HI];
   const float A_lo = __uint_as_float(hdr[H_ALO]), A_hi = __uint_as_float(hdr[H_AHI]);
-  // division-free classification needs the plain eps -> x0 map with a positive alpha
-  const bool num_space = p.param == DPM_PARAM_NOISE && p.predict_x0 && p.alpha_e > 0.f;
+  const bool num_space = qp.num_space != 0;
   const int tid = threadIdx.x;
   if (tid == 0) { s_n = 0; s_lt = 0; }
   __syncthreads();
 
   uint32_t c_lt = 0;
-  // numerator space: 8 elements, ~7 instructions each, no division unless the key is a candidate
+  // numerator space: 8 elements, ~8 instructions each and NO division at all: |num| -> |num / alpha| is
+  // monotone for alpha > 0, so the bracket keys are collected as |num| bit patterns and k_q_finish
+  // selects among them by rank and divides only the two order statistics it returns. One shared-memory
+  // atomic per lane that holds bracket keys (about one lane in six), then predicated stores: with ~2 %
+  // of the keys inside the bracket nearly every warp meets one per packet, so this path is hot.
   auto visit_num8 = [&](const float (&fx)[8], const float (&fc)[8], const float (&fu)[8]) {
-    float num[8];
-    uint32_t mask = 0;
+    float a8[8];
+    uint32_t mask = 0, n_ge = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float eps = (NE == 2) ? fu[i] + p.guidance * (fc[i] - fu[i]) : fc[i];   // :330
-      num[i] = fx[i] - p.sigma_e * eps;                                              // :439 numerator
-      const float a = fabsf(num[i]);
-      const bool ge = a >= A_lo;
-      c_lt += ge ? 0u : 1u;
-      mask |= (ge && a <= A_hi) ? (1u << i) : 0u;
+      a8[i] = fabsf(fx[i] - p.sigma_e * eps);                                        // |numerator| of :439
+      const bool ge = a8[i] >= A_lo;
+      n_ge += ge ? 1u : 0u;
+      mask |= (ge && a8[i] <= A_hi) ? (1u << i) : 0u;
     }
+    c_lt += 8u - n_ge;                                                               // NaN counts as "below", as before
     if (mask) {
+      uint32_t pos = atomicAdd(&s_n, (uint32_t)__popc(mask));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (mask & (1u << i)) {
-          const uint32_t k = __float_as_uint(fabsf(num[i] / p.alpha_e));
-          const uint32_t pos = atomicAdd(&s_n, 1u);
-          if (pos < kLocalCand) lcand[pos] = k;
+          if (pos < kLocalCand) lcand[pos] = __float_as_uint(a8[i]);
+          ++pos;
         }
       }
     }
@@ -421,7 +425,16 @@ __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ 
     __syncthreads();
     key_hi = *min_slot;
   }
-  if (tid == 0) qp.s_out[sample] = finish_value(key_lo, key_hi, qp);
+  if (tid == 0) {
+    uint32_t k_lo = key_lo, k_hi = key_hi;
+    if (bracket_ok && qp.num_space) {
+      // the candidates were |numerator| bit patterns (k_q_count): the order statistics of |x0| are the
+      // IEEE quotients of the selected numerators (monotone map, alpha > 0)
+      k_lo = __float_as_uint(__fdiv_rn(__uint_as_float(key_lo), p.alpha_e));
+      k_hi = __float_as_uint(__fdiv_rn(__uint_as_float(key_hi), p.alpha_e));
+    }
+    qp.s_out[sample] = finish_value(k_lo, k_hi, qp);
+  }
 }
 
 // =================================== B. cluster kernel ==========================================
@@ -662,6 +675,8 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     const uint64_t per_cta = (uint64_t)cu * kPacket * kPThreads * qp.iters;
     qp.slice = (uint32_t)((ps + per_cta - 1) / per_cta);
     qp.work = static_cast<uint32_t*>(workspace);
+    // division-free classification and |numerator| candidates need the plain eps -> x0 map with a positive alpha
+    qp.num_space = (vec && p.param == DPM_PARAM_NOISE && p.predict_x0 && p.alpha_e > 0.f) ? 1u : 0u;
     if (n_samples * qp.slice > 0x7fffffffull) { set_error("too many chunks"); return DPM_ERR_UNSUPPORTED; }
     QKernel kp = p.n_model == 2 ? k_q_pivots<2> : k_q_pivots<1>;
     QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
