@@ -124,9 +124,21 @@ def main():
     pre = os.path.join(SRC, "ncu_summary.md")
     if os.path.exists(pre) and os.path.exists(os.path.join(SRC, "ncu_summary.json")):
         # tools/gpu_round_final.sh summarised the captures on the GPU box (the .ncu-rep files stay there)
-        shutil.copy(pre, os.path.join(DST, f"{R}_ncu_summary.md"))
-        shutil.copy(os.path.join(SRC, "ncu_summary.json"), os.path.join(DST, f"{R}_ncu_summary.json"))
-        md += ["## `ncu --set full` captures (one launch each, `--clock-control none`)", "", open(pre).read().strip(), "",
+        # merge by capture name: a partial round (e.g. only the quantile kernels re-captured) keeps the rest
+        dmd, djs = os.path.join(DST, f"{R}_ncu_summary.md"), os.path.join(DST, f"{R}_ncu_summary.json")
+        rows = OrderedDict()
+        head = []
+        for path in (dmd, pre):
+            if os.path.exists(path):
+                lines = open(path).read().strip().splitlines()
+                head = lines[:2]
+                for l in lines[2:]:
+                    rows[l.split("|")[1].strip()] = l
+        open(dmd, "w").write("\n".join(head + [rows[k] for k in sorted(rows)]) + "\n")
+        js = json.load(open(djs)) if os.path.exists(djs) else {}
+        js.update(json.load(open(os.path.join(SRC, "ncu_summary.json"))))
+        json.dump(js, open(djs, "w"), indent=1)
+        md += ["## `ncu --set full` captures (one launch each, `--clock-control none`)", "", open(dmd).read().strip(), "",
                f"Full metric dump: `profiles/{R}_ncu_summary.json` (incl. stall reasons and SASS mnemonic counts: `UBLKCP` = TMA bulk copy, "
                "`SYNCS` = mbarrier, `LDG.E…256/128` vector loads, `UCGABAR` = cluster barrier).", ""]
     elif reps:
