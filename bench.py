@@ -140,6 +140,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        if self.h is not None and not self.rows:
+            # a timed region shorter than the poller's start-up (a few ms): take one sample right at its end
+            try:
+                nv, h = self.nv, self.h
+                get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get_reasons(h))
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), "0"] +
+                                 [("Active" if r & bit else "Not Active") for bit in (0x8, 0x40, 0x20, 0x4)])
+            except Exception:
+                pass
         self.stop = True
         if self.h is not None and self.thr is not None:
             self.thr.join(timeout=1)
