@@ -94,9 +94,11 @@ class WrappedModel:
 
     def _cond_in(self):
         """cat([unconditional_condition, condition]) (:328); constant over a run, so built once."""
-        key = (id(self.unconditional_condition), id(self.condition))
+        uc, c = self.unconditional_condition, self.condition
+        key = (id(uc), getattr(uc, "_version", 0), id(c), getattr(c, "_version", 0))
         if self._c_in is None or self._c_in[0] != key:
-            self._c_in = (key, torch.cat([self.unconditional_condition, self.condition]))
+            # the pair is kept alive next to the key so that neither id can be recycled
+            self._c_in = (key, torch.cat([uc, c]), (uc, c))
         return self._c_in[1]
 
     def raw(self, x, t_continuous, t_input=None, x_in=None) -> RawOutput:
