@@ -180,7 +180,7 @@ def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, gu
 class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
                  correcting_xt_fn=None, thresholding_max_val=1., dynamic_thresholding_ratio=0.995,
-                 state_dtype=None, plan_broadcast=False):
+                 state_dtype=None, plan_broadcast=False, predict_x0=None, thresholding=None, max_val=None):
         """Same arguments as the reference (:338-347) plus `state_dtype` and `plan_broadcast`:
 
         state_dtype=None keeps the reference's type promotion (fp32 state and buffers even for
@@ -191,7 +191,17 @@ class DPM_Solver:
         plan_broadcast=True (batch-sharded multi-GPU runs, torch.distributed initialised): rank 0
         broadcasts the scalar coefficient plan once per sample() so all ranks use bit-identical
         coefficients (distributed.py); the tensors themselves are never communicated.
+
+        predict_x0 / thresholding / max_val: keyword spelling of the older constructor that the JAX twin
+        still uses (dpm_solver_jax.py:351): predict_x0=True selects "dpmsolver++", thresholding=True
+        (valid with predict_x0) selects dynamic thresholding, max_val is `thresholding_max_val`.
         """
+        if predict_x0 is not None:
+            algorithm_type = "dpmsolver++" if predict_x0 else "dpmsolver"
+        if thresholding:
+            correcting_x0_fn = "dynamic_thresholding"
+        if max_val is not None:
+            thresholding_max_val = max_val
         self._wrapped = model_fn
         self.model = lambda x, t: model_fn(x, t.expand((x.shape[0])))
         self.noise_schedule = noise_schedule

@@ -270,3 +270,18 @@ def test_plan_cache_follows_the_schedule(oracle_backend):
     ns.log_alpha_array.mul_(1.01)                     # in-place edit
     y3 = s.sample(x, steps=10, order=2)
     assert not torch.equal(y3, y2)
+
+
+def test_older_constructor_keywords(oracle_backend):
+    """predict_x0 / thresholding / max_val (the JAX twin's constructor, dpm_solver_jax.py:351) select the
+    same solver as algorithm_type / correcting_x0_fn / thresholding_max_val."""
+    from cases import exact_net, seeded
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    ns = product_schedule("ddpm_linear")
+    x = seeded((2, 3, 8, 8), 3)
+    fn = model_wrapper(exact_net, ns)
+    new = DPM_Solver(fn, ns, algorithm_type="dpmsolver++", correcting_x0_fn="dynamic_thresholding", thresholding_max_val=1.5)
+    old = DPM_Solver(fn, ns, predict_x0=True, thresholding=True, max_val=1.5)
+    assert old.algorithm_type == "dpmsolver++" and old.thresholding_max_val == 1.5
+    np.testing.assert_array_equal(old.sample(x, steps=6, order=2).numpy(), new.sample(x, steps=6, order=2).numpy())
+    assert DPM_Solver(fn, ns, predict_x0=False).algorithm_type == "dpmsolver"
