@@ -252,10 +252,20 @@ class DPM_Solver:
         return torch.float32  # reference promotion: fp32 coefficient tensors make every update fp32
 
     def _state(self, x) -> torch.Tensor:
+        """The tensor the kernels read as `x`. In the reference's promotion mode (state_dtype=None) a
+        16-bit x is widened to fp32 for the arithmetic -- exactly what its fp32 coefficient tensors do --
+        but the NETWORK still receives the caller's 16-bit tensor at that evaluation (only later states
+        are fp32), so the pair is remembered for `_evaluate`."""
         sd = self._sdtype(x)
-        if x.dtype != sd:
-            x = x.to(sd)
-        return x if ops.CudaBackend._layout(x) is not None else x.contiguous()
+        xs = x.to(sd) if x.dtype != sd else x
+        xs = xs if ops.CudaBackend._layout(xs) is not None else xs.contiguous()
+        # (re-evaluations at the same state -- a rejected adaptive step -- must see it again: the pair stays
+        # until the next _state() call or the end of sample())
+        if self.state_dtype is None and x.dtype != sd:
+            self._net_input = (xs, x)
+        elif self.__dict__.get("_net_input") is not None and self._net_input[0] is not xs:
+            self._net_input = None
+        return xs
 
     def _alpha_sigma(self, t_host):
         ns = self.noise_schedule
@@ -265,6 +275,9 @@ class DPM_Solver:
     def _evaluate(self, x, t_dev, t_input=None) -> RawOutput:
         """Call the user's network at (x, t); same call the reference makes through self.model."""
         w = self._wrapped
+        orig = self.__dict__.get("_net_input")
+        if orig is not None and orig[0] is x:
+            x = orig[1]                           # the caller's own (16-bit) tensor, as the reference passes it
         if isinstance(w, WrappedModel) and w.fusable:
             pair = self.__dict__.get("_xin_pair")
             x_in = pair[1] if (pair is not None and pair[0] is x) else None
@@ -850,6 +863,7 @@ class DPM_Solver:
                     x = self.correcting_xt_fn(x, t, step + 1)
                 if return_intermediate:
                     intermediates.append(x)
+        self._net_input = None
         if return_intermediate:
             return x, intermediates
         else:

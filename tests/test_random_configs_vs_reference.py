@@ -169,6 +169,49 @@ def test_random_wide_configurations(oracle_backend, chunk):
             np.testing.assert_array_equal(a.numpy(), b.numpy(), err_msg=str(c))
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_16bit_inputs_follow_the_reference_promotion(oracle_backend, dt):
+    """x handed over in bf16/fp16 (state_dtype=None), discrete schedules, no CFG: the network sees the
+    caller's 16-bit tensor at the first evaluation and fp32 states afterwards, the arithmetic is fp32 on
+    the widened values -- dtype trace and samples bit-identical to the reference. (16-bit CFG outputs and
+    the 0-dim coefficients of the 'linear' schedule are documented deviations)"""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    rng = random.Random(77)
+    done = 0
+    while done < 25:
+        c = draw_wide(rng)
+        if c["method"] == "adaptive" or c["schedule"] == "vp_linear" or c["cfg"] not in (None, 1.0):
+            continue
+        outs = []
+        for mod in (ref, new):
+            _, betas = make_betas(c["schedule"])
+            ns = mod.NoiseScheduleVP("discrete", betas=torch.from_numpy(betas))
+            calls = []
+
+            def net(xx, tt, *cond):
+                calls.append((float(tt[0]), tuple(xx.shape), xx.dtype))
+                return exact_net(xx.float(), tt).to(xx.dtype)
+            if c["cfg"] is not None:
+                fn = mod.model_wrapper(net, ns, model_type=c["model_type"], guidance_type="classifier-free",
+                                       condition=torch.ones(c["B"], 1), unconditional_condition=torch.zeros(c["B"], 1),
+                                       guidance_scale=c["cfg"])
+            else:
+                fn = mod.model_wrapper(net, ns, model_type=c["model_type"])
+            s = mod.DPM_Solver(fn, ns, algorithm_type=c["algo"], correcting_x0_fn="dynamic_thresholding" if c["thresholding"] else None)
+            x = (seeded((c["B"],) + c["shape"], c["seed"]) * c["scale"]).to(dt)
+            y = s.sample(x, steps=c["steps"], order=c["order"], skip_type=c["skip_type"], method=c["method"],
+                         lower_order_final=c["lower_order_final"], denoise_to_zero=c["denoise_to_zero"],
+                         solver_type=c["solver_type"], t_end=c["t_end"], t_start=c["t_start"])
+            outs.append((y, calls))
+        (yr, cr), (yn, cn) = outs
+        if not torch.isfinite(yr).all():
+            continue
+        assert cn == cr, c
+        assert yn.dtype == yr.dtype and torch.equal(yn, yr), c
+        done += 1
+
+
 @pytest.mark.parametrize("model_type", ["noise", "v", "x_start", "score"])
 def test_classifier_guidance_matches_reference(oracle_backend, model_type):
     """guidance_type='classifier' (:315-321): eps - s*sigma_t*grad_x log p(c|x); the guided-diffusion
