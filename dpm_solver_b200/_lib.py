@@ -29,7 +29,7 @@ class StepDesc(C.Structure):
         ("n", C.c_uint64), ("per_sample", C.c_uint64),
         ("state_dtype", C.c_int32), ("model_dtype", C.c_int32), ("form", C.c_int32),
         ("n_model", C.c_int32), ("param", C.c_int32), ("predict_x0", C.c_int32),
-        ("c0_on_old", C.c_int32), ("reserved", C.c_int32),
+        ("c0_on_old", C.c_int32), ("raw_round", C.c_int32),
         ("guidance", C.c_float), ("alpha_e", C.c_float), ("sigma_e", C.c_float),
         ("a", C.c_float), ("c0", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
         ("w0", C.c_float), ("w1", C.c_float), ("w2", C.c_float), ("w3", C.c_float),

@@ -99,6 +99,14 @@ static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for
   if (form < DPM_FORM_NONE || form > DPM_FORM_SS3T) { set_error("bad form %d", form); return DPM_ERR_ARG; }
   if (d->n_model < 0 || d->n_model > 2) { set_error("n_model must be 0, 1 or 2"); return DPM_ERR_ARG; }
   if (d->param < DPM_PARAM_NOISE || d->param > DPM_PARAM_SCORE) { set_error("bad param %d", d->param); return DPM_ERR_ARG; }
+  if (d->raw_round != 0 && ((d->raw_round & ~7) != 0 || ((d->raw_round & 3) != DPM_BF16 && (d->raw_round & 3) != DPM_F16))) {
+    set_error("raw_round must be 0 or (DPM_BF16 | DPM_F16) [+ 4]");
+    return DPM_ERR_ARG;
+  }
+  if (d->raw_round != 0 && (d->state_dtype != DPM_F32 || for_quantile)) {
+    set_error("raw_round needs an fp32 state and is not available in dpm_dynamic_threshold");
+    return DPM_ERR_ARG;
+  }
   if ((d->n >> 3) > 0xffffffffull) { set_error("n too large (max 2^35-1 elements per call)"); return DPM_ERR_ARG; }
 
   nd->x = form != DPM_FORM_NONE;
@@ -158,7 +166,7 @@ static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for
   if (need_alpha) ok = ok && recip_div_ok(d->alpha_e);
   if (need_w4) ok = ok && recip_div_ok(d->w4);
   kp->r_alpha = need_alpha && ok ? 1.0f / d->alpha_e : 0.f;
-  kp->r_sigma = 0.f;
+  kp->raw_round = d->raw_round;
   kp->r_w4 = need_w4 && ok ? 1.0f / d->w4 : 0.f;
   kp->fast_div = ok ? 1 : 0;
   return DPM_OK;
@@ -212,7 +220,7 @@ static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   Tuning t{g_variant.load(), g_threads.load(), g_ctas.load()};
 
   bool body_done = false;
-  if (p.npk > 0 && all_aligned(p, nd)) {
+  if (p.npk > 0 && all_aligned(p, nd) && p.raw_round == 0) {   // reference-rounding mode: generic kernel only
     int r = 1;
     // small launches (a few tiles per SM) gain nothing from the ring; auto keeps them direct
     // fp32 state: direct 256-bit loads sit at the HBM roofline already (fewer instructions per

@@ -49,7 +49,12 @@ struct KParams {
   float w0, w1, w2, w3, w4;
   // correctly rounded reciprocals of the kernel-constant divisors (host computed) and a flag telling
   // the device that the reciprocal-refinement division below is valid for all three of them
-  float r_alpha, r_sigma, r_w4;
+  float r_alpha;
+  // reference-rounding mode (dpm_step_desc.raw_round): bits 0-1 = 16-bit dtype code the raw network
+  // outputs arrived in, bit 2 = buffer differences are taken in that type too. 0 = off. Only the
+  // <RND = true> instantiations below read it.
+  int32_t raw_round;
+  float r_w4;
   int32_t fast_div;
 };
 
@@ -261,13 +266,21 @@ __device__ __forceinline__ float convert_param(int param, float out, float xe, f
 }
 
 // raw network output(s) -> buffered model value (eps, or x0 for dpmsolver++)
-template <int NE>
+// RND: reference-rounding mode. A network that returns 16-bit noise makes the reference evaluate the
+// CFG combine in that type (python-float scale, :329-330): three ops, each rounded to 16 bits.
+template <int NE, bool RND = false>
 __device__ __forceinline__ float model_value(const KParams& p, float xe, float ec, float eu,
                                              float thr, bool clamp) {
   float eps = convert_param(p.param, ec, xe, p.alpha_e, p.sigma_e);
   if (NE == 2) {
     float epu = convert_param(p.param, eu, xe, p.alpha_e, p.sigma_e);
-    eps = epu + p.guidance * (eps - epu);  // model_wrapper.model_fn :330
+    if (RND && p.param == DPM_PARAM_NOISE) {
+      const int dt = p.raw_round & 3;
+      const float d = round_any(dt, eps - epu);
+      eps = round_any(dt, epu + round_any(dt, p.guidance * d));
+    } else {
+      eps = epu + p.guidance * (eps - epu);  // model_wrapper.model_fn :330
+    }
   }
   if (p.predict_x0) {
     float x0 = (xe - p.sigma_e * eps) / p.alpha_e;  // data_prediction_fn :439
@@ -329,9 +342,13 @@ __device__ __forceinline__ void round_pack(Raw<T16>& r, float (&f)[8]) {
 }
 
 // the update. T0 = newest model value, m1/m2 = older buffers.
-template <int FORM>
+// RND: reference-rounding mode, bit 2: the buffered values are raw 16-bit network outputs, so the
+// reference forms their differences (:823, :880-881, :636, :735, :741-742) in that type.
+template <int FORM, bool RND = false>
 __device__ __forceinline__ float update_value(const KParams& p, float x, float T0, float m1,
                                               float m2) {
+  const int ddt = (RND && (p.raw_round & 4)) ? (p.raw_round & 3) : DPM_F32;
+  auto diff = [&](float u, float v) { return RND ? round_any(ddt, u - v) : u - v; };
   if (FORM == DPM_FORM_LIN1) {
     return p.a * x + p.c0 * T0;  // :573-576 / :585-588
   } else if (FORM == DPM_FORM_LIN2) {
@@ -339,18 +356,27 @@ __device__ __forceinline__ float update_value(const KParams& p, float x, float T
   } else if (FORM == DPM_FORM_LIN3) {
     return ((p.a * x + p.c0 * T0) + p.c1 * m1) + p.c2 * m2;
   } else if (FORM == DPM_FORM_DIFF2) {
-    float D = p.w0 * (T0 - m1);              // :823 (w0 = 1/r0) or :639 (w0 = 1)
+    float D = p.w0 * diff(T0, m1);           // :823 (w0 = 1/r0) or :639 (w0 = 1)
     float lead = p.c0_on_old ? m1 : T0;      // singlestep: coefficient sits on model_s
     return (p.a * x + p.c0 * lead) + p.c1 * D;  // :827-851, :636-669, :728-739
   } else if (FORM == DPM_FORM_MS3) {
-    float D10 = p.w0 * (T0 - m1);   // :880
-    float D11 = p.w1 * (m1 - m2);   // :881
+    float D10 = p.w0 * diff(T0, m1);   // :880
+    float D11 = p.w1 * diff(m1, m2);   // :881
     float dd = D10 - D11;
     float D1 = D10 + p.w2 * dd;     // :882
     float D2 = p.w3 * dd;           // :883
     return ((p.a * x + p.c0 * T0) + p.c1 * D1) + p.c2 * D2;  // :888-893 / :898-903
   } else if (FORM == DPM_FORM_SS3T) {
     // m2 = model_s, m1 = model_s1, T0 = model_s2
+    if (RND && (p.raw_round & 4)) {
+      // r1, r2 are python floats or 0-dim tensors (:741-744, :780-783): they do not promote, so with raw
+      // 16-bit buffers the reference evaluates D1 and D2 entirely in that type, one rounding per op
+      auto R = [&](float v) { return round_any(ddt, v); };
+      const float D10 = R(p.w0 * R(m1 - m2)), D11 = R(p.w1 * R(T0 - m2));
+      const float D1 = R(R(R(p.w2 * D10) - R(p.w3 * D11)) / p.w4);
+      const float D2 = R(R(2.f * R(D11 - D10)) / p.w4);
+      return ((p.a * x + p.c0 * m2) + p.c1 * D1) + p.c2 * D2;
+    }
     float D10 = p.w0 * (m1 - m2);                 // :741
     float D11 = p.w1 * (T0 - m2);                 // :742
     float n1 = p.w2 * D10 - p.w3 * D11, n2 = 2.f * (D11 - D10);

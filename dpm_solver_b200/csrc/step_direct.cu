@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kMaxThreads)
 }
 
 // ---- fully generic element-wise kernel: any dtype mix, any alignment, tails ------------------
+// RND = true: reference-rounding mode (common.cuh); the only kernel that implements it so far.
+template <bool RND>
 __global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KParams p) {
   const int sd = p.state_dtype, md = p.model_dtype;
   const bool need_x = p.form != DPM_FORM_NONE;
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KPa
       float ec = load_any(p.ec, md, i);
       float eu = p.n_model == 2 ? load_any(p.eu, md, i) : 0.f;
       float thr = clamp ? p.thr[(i + p.elem_offset) / p.per_sample] : 1.f;
-      float mv = p.n_model == 2 ? model_value<2>(p, xe, ec, eu, thr, clamp)
-                                : model_value<1>(p, xe, ec, eu, thr, clamp);
+      float mv = p.n_model == 2 ? model_value<2, RND>(p, xe, ec, eu, thr, clamp)
+                                : model_value<1, RND>(p, xe, ec, eu, thr, clamp);
       T0 = round_any(sd, mv);
       if (p.m_out) store_any(p.m_out, sd, i, mv);
     } else {
@@ -149,12 +151,12 @@ __global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KPa
     }
     float o;
     switch (p.form) {
-      case DPM_FORM_LIN1: o = update_value<DPM_FORM_LIN1>(p, x, T0, m1, m2); break;
-      case DPM_FORM_LIN2: o = update_value<DPM_FORM_LIN2>(p, x, T0, m1, m2); break;
-      case DPM_FORM_LIN3: o = update_value<DPM_FORM_LIN3>(p, x, T0, m1, m2); break;
-      case DPM_FORM_DIFF2: o = update_value<DPM_FORM_DIFF2>(p, x, T0, m1, m2); break;
-      case DPM_FORM_MS3: o = update_value<DPM_FORM_MS3>(p, x, T0, m1, m2); break;
-      case DPM_FORM_SS3T: o = update_value<DPM_FORM_SS3T>(p, x, T0, m1, m2); break;
+      case DPM_FORM_LIN1: o = update_value<DPM_FORM_LIN1, RND>(p, x, T0, m1, m2); break;
+      case DPM_FORM_LIN2: o = update_value<DPM_FORM_LIN2, RND>(p, x, T0, m1, m2); break;
+      case DPM_FORM_LIN3: o = update_value<DPM_FORM_LIN3, RND>(p, x, T0, m1, m2); break;
+      case DPM_FORM_DIFF2: o = update_value<DPM_FORM_DIFF2, RND>(p, x, T0, m1, m2); break;
+      case DPM_FORM_MS3: o = update_value<DPM_FORM_MS3, RND>(p, x, T0, m1, m2); break;
+      case DPM_FORM_SS3T: o = update_value<DPM_FORM_SS3T, RND>(p, x, T0, m1, m2); break;
       default: continue;
     }
     store_any(p.out, sd, i, o);
@@ -223,7 +225,8 @@ int launch_step_scalar(const KParams& p, cudaStream_t stream) {
   uint64_t blocks = (p.n + threads - 1) / threads;
   uint64_t cap = (uint64_t)sm_count() * 8;
   uint32_t grid = (uint32_t)(blocks < cap ? blocks : cap);
-  k_step_scalar<<<grid, threads, 0, stream>>>(p);
+  if (p.raw_round) k_step_scalar<true><<<grid, threads, 0, stream>>>(p);
+  else k_step_scalar<false><<<grid, threads, 0, stream>>>(p);
   count_launch();
   return 0;
 }

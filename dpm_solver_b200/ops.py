@@ -55,6 +55,7 @@ class StepArgs:
     out: Optional[torch.Tensor] = None     # optional preallocated outputs
     out2: Optional[torch.Tensor] = None    # optional second copy of x_t (doubled CFG batch)
     m_out: Optional[torch.Tensor] = None
+    raw_round: int = 0                # reference-rounding mode (dpm_step_desc.raw_round); 0 = off
 
     def state_tensors(self):
         return [t for t in (self.x, self.xe, self.m0, self.m1, self.m2) if t is not None]
@@ -159,6 +160,7 @@ class CudaBackend:
         d.model_dtype = _DTYPE_CODE[mdt]
         d.form, d.n_model, d.param = a.form, a.n_model, a.param
         d.predict_x0, d.c0_on_old = int(a.predict_x0), int(a.c0_on_old)
+        d.raw_round = int(a.raw_round)
         d.guidance, d.alpha_e, d.sigma_e = a.guidance, a.alpha_e, a.sigma_e
         d.a, d.c0, d.c1, d.c2 = a.a, a.c0, a.c1, a.c2
         d.w0, d.w1, d.w2, d.w3, d.w4 = a.w0, a.w1, a.w2, a.w3, a.w4

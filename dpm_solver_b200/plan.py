@@ -38,6 +38,7 @@ class Coeffs:
     w4: float = 0.0
     c0_on_old: bool = False
     order: int = 1
+    r_tensor: int = 0   # SS3T: bit 0 / 1 = r1 / r2 came as tensors (matters to reference_rounding only)
 
 
 def _cpu(t: torch.Tensor) -> torch.Tensor:
@@ -262,6 +263,7 @@ def singlestep_third(ns, algorithm_type, solver_type, s, t, r1: Number = 1. / 3.
         r1 = 1. / 3.
     if r2 is None:
         r2 = 2. / 3.
+    rt = (1 if torch.is_tensor(r1) else 0) | (2 if torch.is_tensor(r2) else 0)
     s, t = _cpu(s), _cpu(t)
     ms, mt = Marginals(ns, s), Marginals(ns, t)
     h = mt.lam - ms.lam
@@ -286,7 +288,7 @@ def singlestep_third(ns, algorithm_type, solver_type, s, t, r1: Number = 1. / 3.
                          c0_on_old=True, order=3)
         else:
             fin = Coeffs(FORM_SS3T, _f(at), _f(-(gt * phi_1)), _f(gt * phi_2), _f(-(gt * phi_3)),
-                         w0=_f(1. / r1), w1=_f(1. / r2), w2=_f(r2), w3=_f(r1), w4=_f(r2 - r1), order=3)
+                         w0=_f(1. / r1), w1=_f(1. / r2), w2=_f(r2), w3=_f(r1), w4=_f(r2 - r1), order=3, r_tensor=rt)
     else:
         phi_11 = torch.expm1(r1 * h)
         phi_12 = torch.expm1(r2 * h)
@@ -306,7 +308,7 @@ def singlestep_third(ns, algorithm_type, solver_type, s, t, r1: Number = 1. / 3.
                          c0_on_old=True, order=3)
         else:
             fin = Coeffs(FORM_SS3T, _f(at), _f(-(gt * phi_1)), _f(-(gt * phi_2)), _f(-(gt * phi_3)),
-                         w0=_f(1. / r1), w1=_f(1. / r2), w2=_f(r2), w3=_f(r1), w4=_f(r2 - r1), order=3)
+                         w0=_f(1. / r1), w1=_f(1. / r2), w2=_f(r2), w3=_f(r1), w4=_f(r2 - r1), order=3, r_tensor=rt)
     return SinglestepPlan(3, [s, s1, s2], [st1, st2, fin])
 
 

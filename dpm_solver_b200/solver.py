@@ -17,6 +17,7 @@ The order of model evaluations, their (x, t) arguments, the hooks (`correcting_x
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -180,7 +181,8 @@ def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, gu
 class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
                  correcting_xt_fn=None, thresholding_max_val=1., dynamic_thresholding_ratio=0.995,
-                 state_dtype=None, plan_broadcast=False, predict_x0=None, thresholding=None, max_val=None):
+                 state_dtype=None, plan_broadcast=False, predict_x0=None, thresholding=None, max_val=None,
+                 reference_rounding=False):
         """Same arguments as the reference (:338-347) plus `state_dtype` and `plan_broadcast`:
 
         state_dtype=None keeps the reference's type promotion (fp32 state and buffers even for
@@ -191,6 +193,13 @@ class DPM_Solver:
         plan_broadcast=True (batch-sharded multi-GPU runs, torch.distributed initialised): rank 0
         broadcasts the scalar coefficient plan once per sample() so all ranks use bit-identical
         coefficients (distributed.py); the tensors themselves are never communicated.
+
+        reference_rounding=True (opt-in; fp32 state, `model_type="noise"`, network returning bf16/fp16):
+        reproduce the two places where the reference computes in the network's 16-bit output type -- the
+        CFG combine (:329-330, three rounded ops) and, for the eps-solver, the differences of the
+        buffered raw outputs (:823, :880-881, :636, :735, :741-742). Default False: both are evaluated in
+        fp32 on the widened values (closer to the exact result, and the fast kernels). Runs on the generic
+        kernel for now.
 
         predict_x0 / thresholding / max_val: keyword spelling of the older constructor that the JAX twin
         still uses (dpm_solver_jax.py:351): predict_x0=True selects "dpmsolver++", thresholding=True
@@ -220,6 +229,8 @@ class DPM_Solver:
             raise TypeError("state_dtype must be one of {}".format(ops.SUPPORTED_DTYPES))
         self.state_dtype = state_dtype
         self.plan_broadcast = bool(plan_broadcast)
+        self.reference_rounding = bool(reference_rounding)
+        self._rr_run = 0     # raw_round of the buffered values of the run in flight (reference_rounding)
 
     def _sync_plan(self, coeffs, key=None):
         """Rank 0's coefficients on every rank. One broadcast per sampling configuration: the synced
@@ -378,6 +389,30 @@ class DPM_Solver:
     def _needs_conversion(raw: RawOutput, sdtype, x0: bool) -> bool:
         return x0 or raw.e_uncond is not None or raw.param != PARAM_NOISE or raw.e_cond.dtype != sdtype
 
+    _RR_CODE = {torch.bfloat16: 1, torch.float16: 2}      # dpm_dtype codes carried by raw_round
+
+    def _rr_code(self, raw: RawOutput) -> int:
+        """16-bit dtype code of raw NOISE outputs in reference-rounding mode, else 0."""
+        if not self.reference_rounding or self.state_dtype is not None or raw.param != PARAM_NOISE:
+            return 0
+        return self._RR_CODE.get(raw.e_cond.dtype, 0)
+
+    @staticmethod
+    def _rr_coeffs(co: P.Coeffs, code: int) -> P.Coeffs:
+        """singlestep-3 'taylor' (:780-783) in reference-rounding mode: r1, r2 that arrive as 0-dim tensors
+        (the sample() loop, :1223-1227) are cast to the buffers' 16-bit type where they are the LEFT operand
+        of a product (`(1./r1) * (..)`, `r2 * D1_0`, `r1 * D1_1`); python floats (the defaults of the
+        directly called method) and right-hand scalars (the divisor `r2 - r1`) enter in fp32 -- torch's CPU
+        kernels keep the second operand of mul/div in the op's fp32 math type when it is a scalar."""
+        if co.form != FORM_SS3T or not co.r_tensor:
+            return co
+        T = torch.bfloat16 if code == 1 else torch.float16
+        rT = lambda v: float(torch.tensor(v, dtype=torch.float32).to(T))
+        r1t, r2t = bool(co.r_tensor & 1), bool(co.r_tensor & 2)
+        return dataclasses.replace(co, w0=rT(co.w0) if r1t else co.w0, w1=rT(co.w1) if r2t else co.w1,
+                                   w2=rT(co.w2) if r2t else co.w2, w3=rT(co.w3) if r1t else co.w3,
+                                   w4=co.w4)
+
     def _post_model(self, raw: RawOutput, xe, t_dev, alsig, co: Optional[P.Coeffs] = None, x=None,
                     m1=None, m2=None, want_m: bool = True, dup_out: bool = False, x0: Optional[bool] = None):
         """The fused post-model step: buffered value from `raw` (+ optional update `co`).
@@ -388,9 +423,23 @@ class DPM_Solver:
         x0 = self._pp if x0 is None else x0          # buffered value: x0 (dpmsolver++ / data_prediction_fn) or eps
         sd = xe.dtype if xe is not None else (x.dtype if x is not None else raw.e_cond.dtype)
         custom_fix = x0 and self.correcting_x0_fn is not None and not self._dynamic_thresholding
+        code = self._rr_code(raw)
+        rr = 0
+        if code:
+            if raw.e_uncond is not None:
+                # the reference's 16-bit CFG combine, materialised (values exactly representable in the
+                # network's type, held in fp32); everything downstream then sees a single noise tensor
+                e = be.step(StepArgs(form=FORM_NONE, n_model=2, e_cond=raw.e_cond, e_uncond=raw.e_uncond,
+                                     param=PARAM_NOISE, guidance=raw.guidance, state_dtype=torch.float32,
+                                     raw_round=code))[0]
+                raw = RawOutput(e, None, PARAM_NOISE, 1.0)
+            if not x0:
+                rr = self._rr_run = code | 4       # eps-solver: the buffers are raw 16-bit outputs
+        if rr and co is not None:
+            co = self._rr_coeffs(co, code)
         if not self._needs_conversion(raw, sd, x0):
             m_new = raw.e_cond if ops.CudaBackend._layout(raw.e_cond) is not None else raw.e_cond.contiguous()
-            x_next = self._pure_update(co, x, m_new, m1, m2) if co is not None else None
+            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr) if co is not None else None
             return m_new, x_next
         a = self._conv_args(raw, xe, alsig, sd, x0)
         if x0 and self._dynamic_thresholding:
@@ -402,10 +451,11 @@ class DPM_Solver:
             m_new = be.step(a)[0]
             if custom_fix:
                 m_new = self._state_like(self.correcting_x0_fn(m_new, t_dev), sd)
-            x_next = self._pure_update(co, x, m_new, m1, m2) if co is not None else None
+            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr) if co is not None else None
             return m_new, x_next
         self._fill_update(a, co, x, m1, m2)
         a.want_m_out = want_m
+        a.raw_round = rr
         dup = self._dup_target(x) if dup_out else None
         if dup is not None:
             a.out, a.out2 = dup[1], dup[2]
@@ -427,8 +477,15 @@ class DPM_Solver:
         a.w0, a.w1, a.w2, a.w3, a.w4 = co.w0, co.w1, co.w2, co.w3, co.w4
         a.c0_on_old = co.c0_on_old
 
-    def _pure_update(self, co: P.Coeffs, x, m0, m1=None, m2=None):
-        a = StepArgs(n_model=0, m0=self._state_like(m0, x.dtype), state_dtype=x.dtype)
+    def _pure_update(self, co: P.Coeffs, x, m0, m1=None, m2=None, rr: Optional[int] = None):
+        if rr is None:
+            # directly called update methods: buffers handed over in one 16-bit type are raw outputs
+            rr = 0
+            dts = {m.dtype for m in (m0, m1, m2) if m is not None}
+            if (self.reference_rounding and self.state_dtype is None and x.dtype == torch.float32
+                    and len(dts) == 1 and next(iter(dts)) in self._RR_CODE):
+                rr = self._RR_CODE[next(iter(dts))] | 4
+        a = StepArgs(n_model=0, m0=self._state_like(m0, x.dtype), state_dtype=x.dtype, raw_round=rr)
         self._fill_update(a, co, x, None if m1 is None else self._state_like(m1, x.dtype),
                           None if m2 is None else self._state_like(m2, x.dtype))
         return ops.backend().step(a)[1]
@@ -563,7 +620,7 @@ class DPM_Solver:
             if given is not None:
                 # caller supplied this model value (the adaptive solver reuses the lower-order ones)
                 if not skip_update:
-                    x_next = self._pure_update(co, x, given, m1, m2)
+                    x_next = self._pure_update(co, x, given, m1, m2, rr=self._rr_run)
             else:
                 raw = self._evaluate(xe, td[j], tin[j])
                 want = keep or (not last and (j == 0 or taylor3))
@@ -743,6 +800,7 @@ class DPM_Solver:
         intermediates = []
         ns = self.noise_schedule
         self._xin_pair = None
+        self._rr_run = 0
         with torch.no_grad():
             x = self._state(x)
             sd = x.dtype

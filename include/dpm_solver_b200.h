@@ -114,7 +114,12 @@ typedef struct dpm_step_desc {
   int32_t param;       /* dpm_param                                                        */
   int32_t predict_x0;  /* 1: buffered value is x0 = (xe - sigma_e*eps)/alpha_e :439         */
   int32_t c0_on_old;   /* DIFF2 only                                                       */
-  int32_t reserved;
+  int32_t raw_round;   /* 0 (default). Reference-rounding mode for networks that return 16-bit NOISE into an
+                          fp32 state: bits 0-1 = DPM_BF16 / DPM_F16, the type the raw outputs arrived in --
+                          the CFG combine :329-330 then rounds to it after each of its three ops, as the
+                          reference's eager 16-bit ops do; bit 2 (+4) = the buffered values are such raw
+                          outputs, so their differences (:823, :880-881, :636, :735, :741-742) are rounded
+                          to that type before the fp32 coefficients widen them. Generic kernel only.   */
   float guidance;      /* CFG scale s: eps = eps_u + s*(eps_c - eps_u) :330                */
   float alpha_e;       /* alpha, sigma at the model evaluation time                         */
   float sigma_e;

@@ -23,6 +23,7 @@ from dpm_solver_b200._lib import (FORM_DIFF2, FORM_LIN1, FORM_LIN2, FORM_LIN3, F
                                   FORM_SS3T, PARAM_SCORE, PARAM_V, PARAM_X_START)
 
 f32 = np.float32
+_RR_DTYPE = {1: torch.bfloat16, 2: torch.float16}   # dpm_dtype codes carried by raw_round
 
 
 def _np(t):
@@ -66,7 +67,14 @@ class OracleBackend:
         eps = self._convert(a, ec, xe)
         if a.n_model == 2:
             epu = self._convert(a, eu, xe)
-            eps = epu + f32(a.guidance) * (eps - epu)
+            rr = getattr(a, "raw_round", 0)
+            if rr and a.param not in (PARAM_X_START, PARAM_V, PARAM_SCORE):
+                # reference-rounding mode (dpm_step_desc.raw_round): three 16-bit ops
+                dt = _RR_DTYPE[rr & 3]
+                d = _round((eps - epu).astype(f32), dt)
+                eps = _round((epu + _round((f32(a.guidance) * d).astype(f32), dt)).astype(f32), dt)
+            else:
+                eps = epu + f32(a.guidance) * (eps - epu)
         if a.predict_x0:
             x0 = (xe - f32(a.sigma_e) * eps) / f32(a.alpha_e)
             if thr is not None:
@@ -96,6 +104,8 @@ class OracleBackend:
             x, m1, m2 = _np(a.x), _np(a.m1), _np(a.m2)
             A, c0, c1, c2 = f32(a.a), f32(a.c0), f32(a.c1), f32(a.c2)
             w0, w1, w2, w3, w4 = (f32(v) for v in (a.w0, a.w1, a.w2, a.w3, a.w4))
+            rr = getattr(a, "raw_round", 0)
+            diff = (lambda u, v: _round((u - v).astype(f32), _RR_DTYPE[rr & 3])) if rr & 4 else (lambda u, v: u - v)
             if a.form == FORM_LIN1:
                 o = A * x + c0 * T0
             elif a.form == FORM_LIN2:
@@ -103,18 +113,24 @@ class OracleBackend:
             elif a.form == FORM_LIN3:
                 o = ((A * x + c0 * T0) + c1 * m1) + c2 * m2
             elif a.form == FORM_DIFF2:
-                D = w0 * (T0 - m1)
+                D = w0 * diff(T0, m1)
                 o = (A * x + c0 * (m1 if a.c0_on_old else T0)) + c1 * D
             elif a.form == FORM_MS3:
-                D10 = w0 * (T0 - m1)
-                D11 = w1 * (m1 - m2)
+                D10 = w0 * diff(T0, m1)
+                D11 = w1 * diff(m1, m2)
                 dd = D10 - D11
                 o = ((A * x + c0 * T0) + c1 * (D10 + w2 * dd)) + c2 * (w3 * dd)
             elif a.form == FORM_SS3T:
-                D10 = w0 * (m1 - m2)
-                D11 = w1 * (T0 - m2)
-                D1 = (w2 * D10 - w3 * D11) / w4
-                D2 = (f32(2) * (D11 - D10)) / w4
+                if rr & 4:      # python-float / 0-dim r1, r2 do not promote: D1, D2 entirely in the 16-bit type
+                    R = lambda v: _round(np.asarray(v, dtype=f32), _RR_DTYPE[rr & 3])
+                    D10, D11 = R(w0 * R(m1 - m2)), R(w1 * R(T0 - m2))
+                    D1 = R(R(R(w2 * D10) - R(w3 * D11)) / w4)
+                    D2 = R(R(f32(2) * R(D11 - D10)) / w4)
+                else:
+                    D10 = w0 * (m1 - m2)
+                    D11 = w1 * (T0 - m2)
+                    D1 = (w2 * D10 - w3 * D11) / w4
+                    D2 = (f32(2) * (D11 - D10)) / w4
                 o = ((A * x + c0 * m2) + c1 * D1) + c2 * D2
             else:
                 raise ValueError(a.form)

@@ -212,6 +212,55 @@ def test_16bit_inputs_follow_the_reference_promotion(oracle_backend, dt):
         done += 1
 
 
+@pytest.mark.parametrize("x_16bit", [False, True], ids=["x_fp32", "x_16bit"])
+def test_reference_rounding_mode_is_bit_identical(oracle_backend, x_16bit):
+    """`DPM_Solver(..., reference_rounding=True)`: a network that returns bf16/fp16 makes the reference
+    evaluate the CFG combine (:329-330) and, in the eps-solver, the differences of the buffered raw
+    outputs -- for singlestep-3 'taylor' the whole D1/D2 chain (:780-783) -- in that 16-bit type. With
+    the option on, samples are bit-identical to the reference for every parameterisation, with and
+    without CFG (scales that are not representable in bf16 included), fp32 or 16-bit x_T."""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    rng = random.Random(4242 + int(x_16bit))
+    done = 0
+    while done < 30:
+        c = draw_wide(rng)
+        if c["method"] == "adaptive" or c["schedule"] == "vp_linear":
+            continue
+        dt = rng.choice([torch.bfloat16, torch.float16])
+        if c["cfg"] not in (None, 1.0) and rng.random() < 0.5:
+            c["cfg"] = rng.choice([3.7, 2.3, 9.1])
+        outs = []
+        for mod in (ref, new):
+            _, betas = make_betas(c["schedule"])
+            ns = mod.NoiseScheduleVP("discrete", betas=torch.from_numpy(betas))
+
+            def net(xx, tt, *cond):
+                o = exact_net(xx.float(), tt)
+                if cond:
+                    o = o + 0.05 * cond[0].reshape(-1, 1, 1, 1)
+                return o.to(dt)
+            if c["cfg"] is not None:
+                fn = mod.model_wrapper(net, ns, model_type=c["model_type"], guidance_type="classifier-free",
+                                       condition=torch.ones(c["B"], 1), unconditional_condition=torch.zeros(c["B"], 1),
+                                       guidance_scale=c["cfg"])
+            else:
+                fn = mod.model_wrapper(net, ns, model_type=c["model_type"])
+            kw = dict(reference_rounding=True) if mod is new else {}
+            s = mod.DPM_Solver(fn, ns, algorithm_type=c["algo"],
+                               correcting_x0_fn="dynamic_thresholding" if c["thresholding"] else None, **kw)
+            x = seeded((c["B"],) + c["shape"], c["seed"]) * c["scale"]
+            y = s.sample(x.to(dt) if x_16bit else x, steps=c["steps"], order=c["order"], skip_type=c["skip_type"],
+                         method=c["method"], lower_order_final=c["lower_order_final"], denoise_to_zero=c["denoise_to_zero"],
+                         solver_type=c["solver_type"], t_end=c["t_end"], t_start=c["t_start"])
+            outs.append(y)
+        yr, yn = outs
+        if not torch.isfinite(yr).all():
+            continue
+        assert yn.dtype == yr.dtype and torch.equal(yn, yr), (c, dt)
+        done += 1
+
+
 @pytest.mark.parametrize("model_type", ["noise", "v", "x_start", "score"])
 def test_classifier_guidance_matches_reference(oracle_backend, model_type):
     """guidance_type='classifier' (:315-321): eps - s*sigma_t*grad_x log p(c|x); the guided-diffusion
