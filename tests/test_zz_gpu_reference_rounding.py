@@ -78,3 +78,27 @@ def test_reference_rounding_sample_equals_executor(cuda_backend, oracle_backend_
     y = run(DEV)
     ops.set_backend(oracle_backend_cpu)
     assert torch.equal(y.cpu(), run("cpu"))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_16bit_x_promotion_mode_equals_executor(cuda_backend, oracle_backend_cpu, dt):
+    """x_T handed over in 16 bits with state_dtype=None (staged with the rest of this file): the network sees the
+    16-bit tensor at the first evaluation, fp32 afterwards; CUDA path == numpy executor, bit for bit."""
+    from cases import exact_net, make_betas, seeded
+    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper, ops
+
+    def run(device):
+        ns = NoiseScheduleVP("discrete", betas=torch.from_numpy(make_betas("sd")[1]))
+        seen = []
+
+        def net(xx, tt):
+            seen.append(xx.dtype)
+            return exact_net(xx.float(), tt).to(xx.dtype)
+        s = DPM_Solver(model_wrapper(net, ns), ns, algorithm_type="dpmsolver++")
+        y = s.sample(seeded((3, 4, 16, 16), 12).to(dt).to(device), steps=8, order=3)
+        return y, seen
+
+    y, seen = run(DEV)
+    assert seen[0] == dt and all(d == torch.float32 for d in seen[1:]) and y.dtype == torch.float32
+    ops.set_backend(oracle_backend_cpu)
+    assert torch.equal(y.cpu(), run("cpu")[0])
