@@ -214,6 +214,11 @@ class DPM_Solver:
         self._wrapped = model_fn
         self.model = lambda x, t: model_fn(x, t.expand((x.shape[0])))
         self.noise_schedule = noise_schedule
+        tables = getattr(noise_schedule, "log_alpha_array", None)
+        if torch.is_tensor(tables) and tables.dtype != torch.float32:
+            # the reference would promote x and every update to that dtype; there are no fp64 kernels
+            raise TypeError("dpm_solver_b200 computes in fp32: NoiseScheduleVP(dtype={}) is not supported "
+                            "by DPM_Solver".format(tables.dtype))
         assert algorithm_type in ["dpmsolver", "dpmsolver++"]
         self.algorithm_type = algorithm_type
         if correcting_x0_fn == "dynamic_thresholding":

@@ -285,3 +285,13 @@ def test_older_constructor_keywords(oracle_backend):
     assert old.algorithm_type == "dpmsolver++" and old.thresholding_max_val == 1.5
     np.testing.assert_array_equal(old.sample(x, steps=6, order=2).numpy(), new.sample(x, steps=6, order=2).numpy())
     assert DPM_Solver(fn, ns, predict_x0=False).algorithm_type == "dpmsolver"
+
+
+def test_non_fp32_schedule_is_rejected():
+    """NoiseScheduleVP(dtype=float64) makes the reference promote x and every update to fp64; there are no
+    fp64 kernels, so the solver refuses instead of silently answering in fp32."""
+    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP
+    ns = NoiseScheduleVP("discrete", betas=torch.from_numpy(make_betas("sd")[1]), dtype=torch.float64)
+    assert ns.log_alpha_array.dtype == torch.float64        # the schedule object itself follows the reference
+    with pytest.raises(TypeError, match="fp32"):
+        DPM_Solver(lambda x, t: x, ns)
