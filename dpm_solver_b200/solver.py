@@ -121,14 +121,23 @@ class WrappedModel:
         raise RuntimeError("raw() is not available with classifier guidance")
 
     def _alpha_sigma(self, t_continuous):
-        """Host scalars (alpha_t, sigma_t); all labels of a batch must be equal."""
-        tc = t_continuous.detach().reshape(-1)
-        t0 = tc[:1].cpu()
-        if tc.numel() > 1 and not bool((tc == tc[0]).all()):
-            raise NotImplementedError("dpm_solver_b200: per-sample time labels are not supported by "
-                                      "the fused model_wrapper; call it with a single time per batch")
+        """Host scalars [(alpha_t, sigma_t)]: one pair when all labels of the batch are equal (the solver's
+        case), else one pair per sample (model_fn called directly with a vector of different times)."""
+        tc = t_continuous.detach().reshape(-1).cpu()
         ns = self.noise_schedule
-        return float(ns.marginal_alpha(t0)), float(ns.marginal_std(t0))
+        if tc.numel() > 1 and not bool((tc == tc[0]).all()):
+            return list(zip(ns.marginal_alpha(tc).tolist(), ns.marginal_std(tc).tolist()))
+        t0 = tc[:1]
+        return [(float(ns.marginal_alpha(t0)), float(ns.marginal_std(t0)))]
+
+    @staticmethod
+    def _per_sample(pairs, batch, launch):
+        """Run `launch(rows, alpha, sigma)` once for the whole batch, or once per sample when the time labels
+        differ (alpha_t, sigma_t are launch constants of the kernels)."""
+        if len(pairs) == 1:
+            return launch(slice(None), *pairs[0])
+        assert len(pairs) == batch, "one time label per sample expected"
+        return torch.cat([launch(slice(i, i + 1), al, sg) for i, (al, sg) in enumerate(pairs)])
 
     def __call__(self, x, t_continuous):
         be = ops.backend()
@@ -139,27 +148,35 @@ class WrappedModel:
                 x_in = x.detach().requires_grad_(True)
                 log_prob = self.classifier_fn(x_in, t_input, self.condition, **self.classifier_kwargs)
                 cond_grad = torch.autograd.grad(log_prob.sum(), x_in)[0]
-            alpha, sigma = self._alpha_sigma(t_continuous)
+            pairs = self._alpha_sigma(t_continuous)
             out = self._call_model(x, t_continuous)
             param = PARAM_BY_NAME[self.model_type]
-            if param != PARAM_NOISE:
-                out = be.step(StepArgs(form=FORM_NONE, n_model=1, e_cond=out, xe=x.to(out.dtype), param=param,
-                                       alpha_e=alpha, sigma_e=sigma, state_dtype=out.dtype))[0]
-            # noise - guidance_scale * sigma_t * cond_grad (:321); (s*sigma) is formed in fp32 first
-            gs = float(torch.tensor(sigma, dtype=torch.float32) * self.guidance_scale)
-            return ops.lincomb(out, [cond_grad.to(out.dtype)], 1.0, [-gs])
+            xo, grad = x.to(out.dtype), cond_grad.to(out.dtype)
+
+            def guided(rows, alpha, sigma):
+                o = out[rows]
+                if param != PARAM_NOISE:
+                    o = be.step(StepArgs(form=FORM_NONE, n_model=1, e_cond=o, xe=xo[rows], param=param,
+                                         alpha_e=alpha, sigma_e=sigma, state_dtype=out.dtype))[0]
+                # noise - guidance_scale * sigma_t * cond_grad (:321); (s*sigma) is formed in fp32 first
+                gs = float(torch.tensor(sigma, dtype=torch.float32) * self.guidance_scale)
+                return ops.lincomb(o, [grad[rows]], 1.0, [-gs])
+            return self._per_sample(pairs, x.shape[0], guided)
         r = self.raw(x, t_continuous)
         if r.e_uncond is None and r.param == PARAM_NOISE:
             return r.e_cond
-        alpha, sigma = (1.0, 0.0)
-        if r.param != PARAM_NOISE:
-            alpha, sigma = self._alpha_sigma(t_continuous)
-        a = StepArgs(form=FORM_NONE, n_model=2 if r.e_uncond is not None else 1, e_cond=r.e_cond,
-                     e_uncond=r.e_uncond, param=r.param, guidance=r.guidance, alpha_e=alpha,
-                     sigma_e=sigma, state_dtype=r.e_cond.dtype)
-        if r.param in (PARAM_BY_NAME["x_start"], PARAM_BY_NAME["v"]):
-            a.xe = x.to(r.e_cond.dtype)
-        return be.step(a)[0]
+        pairs = self._alpha_sigma(t_continuous) if r.param != PARAM_NOISE else [(1.0, 0.0)]
+        needs_x = r.param in (PARAM_BY_NAME["x_start"], PARAM_BY_NAME["v"])
+        xo = x.to(r.e_cond.dtype) if needs_x else None
+
+        def convert(rows, alpha, sigma):
+            a = StepArgs(form=FORM_NONE, n_model=2 if r.e_uncond is not None else 1, e_cond=r.e_cond[rows],
+                         e_uncond=None if r.e_uncond is None else r.e_uncond[rows], param=r.param,
+                         guidance=r.guidance, alpha_e=alpha, sigma_e=sigma, state_dtype=r.e_cond.dtype)
+            if needs_x:
+                a.xe = xo[rows]
+            return be.step(a)[0]
+        return self._per_sample(pairs, x.shape[0], convert)
 
 
 def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, guidance_type="uncond",

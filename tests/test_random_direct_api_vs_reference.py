@@ -84,3 +84,39 @@ def test_direct_api_bit_exact(oracle_backend, chunk):
         assert len(a) == len(b), c
         for u, v in zip(a, b):
             np.testing.assert_array_equal(v.numpy(), u.numpy(), err_msg=str(c))
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_model_fn_with_per_sample_times(oracle_backend, chunk):
+    """`model_fn(x, t_continuous)` called directly with a VECTOR of different times (the reference's wrapper
+    accepts it for every parameterisation and guidance type, :282-330): bit-identical."""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    for seed in range(40 * chunk, 40 * (chunk + 1)):
+        rng = random.Random(seed)
+        sched = rng.choice(["sd", "ddpm_linear", "iddpm_cosine", "vp_linear"])
+        mt = rng.choice(["noise", "v", "x_start", "score"])
+        g = rng.choice(["uncond", "classifier-free", "classifier"])
+        scale = rng.choice([1.0, 3.5, 7.5, 2.3])
+        B = rng.choice([1, 2, 4])
+        tt = (torch.full((B,), rng.uniform(0.01, 1.0)) if rng.random() < 0.3
+              else torch.tensor([rng.uniform(0.01, 1.0) for _ in range(B)]))
+        x = seeded((B, 3, 8, 8), seed)
+        outs = []
+        for mod in (ref, new):
+            kind, betas = make_betas(sched)
+            ns = mod.NoiseScheduleVP("linear") if kind == "linear" else mod.NoiseScheduleVP("discrete", betas=torch.from_numpy(betas))
+            if g == "uncond":
+                fn = mod.model_wrapper(lambda xx, t: exact_net(xx, t), ns, model_type=mt)
+            elif g == "classifier-free":
+                fn = mod.model_wrapper(lambda xx, t, c: exact_net(xx, t) + 0.05 * c.reshape(-1, 1, 1, 1), ns, model_type=mt,
+                                       guidance_type="classifier-free", condition=torch.ones(B, 1),
+                                       unconditional_condition=torch.zeros(B, 1), guidance_scale=scale)
+            else:
+                def cls(xx, t_in, cond, **kw):
+                    return -((xx - 0.1 * cond.reshape(-1, 1, 1, 1)) ** 2).flatten(1).sum(1) * 0.01 + 0 * t_in
+                fn = mod.model_wrapper(lambda xx, t: exact_net(xx, t), ns, model_type=mt, guidance_type="classifier",
+                                       condition=torch.ones(B), guidance_scale=scale, classifier_fn=cls)
+            outs.append(fn(x, tt))
+        a, b = outs
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), (sched, mt, g, scale)
