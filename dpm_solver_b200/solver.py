@@ -18,6 +18,7 @@ The order of model evaluations, their (x, t) arguments, the hooks (`correcting_x
 from __future__ import annotations
 
 import dataclasses
+import inspect
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -242,7 +243,7 @@ class DPM_Solver:
             self.correcting_x0_fn = self.dynamic_thresholding_fn
             self._dynamic_thresholding = True
         else:
-            self.correcting_x0_fn = correcting_x0_fn
+            self.correcting_x0_fn = self._x0_hook(correcting_x0_fn)
             self._dynamic_thresholding = False
         self.correcting_xt_fn = correcting_xt_fn
         self.dynamic_thresholding_ratio = dynamic_thresholding_ratio
@@ -253,6 +254,22 @@ class DPM_Solver:
         self.plan_broadcast = bool(plan_broadcast)
         self.reference_rounding = bool(reference_rounding)
         self._rr_run = 0     # raw_round of the buffered values of the run in flight (reference_rounding)
+
+    @staticmethod
+    def _x0_hook(fn):
+        """`correcting_x0_fn(x0, t)` (:379-380). The older vendored copy calls it with x0 only
+        (examples/stable-diffusion/.../dpm_solver.py:447-448); a one-argument callable keeps working."""
+        if fn is None or not callable(fn):
+            return fn
+        try:
+            params = [p for p in inspect.signature(fn).parameters.values()
+                      if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+            variadic = any(p.kind == p.VAR_POSITIONAL for p in inspect.signature(fn).parameters.values())
+        except (TypeError, ValueError):
+            return fn
+        if len(params) == 1 and not variadic:
+            return lambda x0, t: fn(x0)
+        return fn
 
     def _sync_plan(self, coeffs, key=None):
         """Rank 0's coefficients on every rank. One broadcast per sampling configuration: the synced

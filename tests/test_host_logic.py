@@ -295,3 +295,16 @@ def test_non_fp32_schedule_is_rejected():
     assert ns.log_alpha_array.dtype == torch.float64        # the schedule object itself follows the reference
     with pytest.raises(TypeError, match="fp32"):
         DPM_Solver(lambda x, t: x, ns)
+
+
+def test_one_argument_x0_corrector(oracle_backend):
+    """The older vendored solver copy calls `correcting_x0_fn(x0)` (examples/stable-diffusion/.../dpm_solver.py
+    :447-448): a one-argument callable is accepted and gives the same result as its two-argument spelling."""
+    from cases import exact_net, seeded
+    from dpm_solver_b200 import DPM_Solver, model_wrapper
+    ns = product_schedule("sd")
+    x = seeded((2, 3, 8, 8), 9)
+    fn = model_wrapper(exact_net, ns)
+    y1 = DPM_Solver(fn, ns, correcting_x0_fn=lambda x0: x0.clamp(-1, 1)).sample(x, steps=5, order=2)
+    y2 = DPM_Solver(fn, ns, correcting_x0_fn=lambda x0, t: x0.clamp(-1, 1)).sample(x, steps=5, order=2)
+    np.testing.assert_array_equal(y1.numpy(), y2.numpy())
