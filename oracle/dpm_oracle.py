@@ -539,6 +539,14 @@ class Sampler:
         t_in = model_input_time(self.ns, xp.cat([t1] * (2 * B)))   # :327
         if self.log_calls:
             self.calls.append((float(t_in[0]), tuple(x2.shape)))
+        if self.scale == 1.:
+            # :323-324: a scale of exactly 1 bypasses the combine -- the reference evaluates the conditional
+            # branch alone. This two-argument `net` only reaches that branch through the doubled batch, so
+            # the batch is still doubled here and the conditional half returned unchanged (same values for
+            # a per-sample network); the call is logged with the shape the reference's single call has.
+            if self.log_calls:
+                self.calls[-1] = (float(t_in[0]), tuple(x.shape))
+            return to_noise(self.ns, self.model_type, x2, self.net(x2, t_in), t1)[B:]
         both = to_noise(self.ns, self.model_type, x2, self.net(x2, t_in), t1)
         return cfg_combine(both[:B], both[B:], self.scale)          # :329-330, uncond half first
 
