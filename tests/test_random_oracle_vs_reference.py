@@ -30,7 +30,9 @@ def test_oracle_matches_reference_on_random_configurations(chunk):
         if not torch.isfinite(yr).all():
             continue
         yt, _, _ = helpers.run_oracle_case(case, None, O.torch_namespace("cpu"))
-        np.testing.assert_array_equal(yt.numpy(), yr.numpy(), err_msg=str(case))
+        yt = yt.numpy() if torch.is_tensor(yt) else np.asarray(yt)
+        np.testing.assert_array_equal(yt, yr.numpy(), err_msg=str(case))
         yn, _, _ = helpers.run_oracle_case(case, None, O.NP)
+        yn = yn.numpy() if torch.is_tensor(yn) else np.asarray(yn)
         assert helpers.rel_err(yn, yr.numpy()) <= 1e-3, case
         done += 1
