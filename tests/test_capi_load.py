@@ -65,3 +65,37 @@ def test_cpu_tensors_are_refused():
     be = ops.CudaBackend()
     with pytest.raises(RuntimeError, match="CUDA-only"):
         be.step(ops.StepArgs(form=1, x=torch.zeros(8), m0=torch.zeros(8), a=1.0, c0=1.0))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/dpm_solver_b200.h compiles as C99 (-pedantic) and a C program links against the library and calls
+    it without a GPU: the boundary really is a C-ABI, not a C++ or torch interface."""
+    import shutil
+    import subprocess
+    from dpm_solver_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "dpm_solver_b200.h"
+int main(void) {
+  dpm_step_desc d;
+  memset(&d, 0, sizeof d);
+  if (dpm_version() != DPM_B200_VERSION) return 1;
+  if (dpm_step(NULL, NULL) != DPM_ERR_ARG || strstr(dpm_last_error(), "NULL") == NULL) return 2;
+  if (dpm_step(&d, NULL) != DPM_OK) return 3;             /* n == 0: nothing to do */
+  d.n = 16; d.form = DPM_FORM_MS3;
+  if (dpm_step(&d, NULL) != DPM_ERR_ARG) return 4;         /* tensors missing */
+  printf("%zu\n", sizeof d);
+  return 0;
+}
+""")
+    exe = tmp_path / "client"
+    libdir = str(_lib.LIB_PATH.parent) if hasattr(_lib.LIB_PATH, "parent") else os.path.dirname(str(_lib.LIB_PATH))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-ldpmsolver_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert int(r.stdout.strip()) == C.sizeof(_lib.StepDesc)
