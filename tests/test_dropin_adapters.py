@@ -1,84 +1,129 @@
-"""T5 drop-in acceptance: the reference's own Stable-Diffusion adapter (DPMSolverSampler,
-examples/stable-diffusion/ldm/models/diffusion/dpm_solver/sampler.py) is executed UNMODIFIED twice --
-once on top of its vendored copy of the solver, once on top of dpm_solver_b200 -- with a stub
-LatentDiffusion model. Outputs (sample, every intermediate, stochastic_encode) must be bit-identical.
-Needs /root/reference (build container only); skipped elsewhere."""
-import importlib.util
+"""T5 drop-in acceptance: the reference's three example adapters (Stable Diffusion `DPMSolverSampler`, score_sde
+`get_dpm_solver_sampler`, guided-diffusion `Diffusion.sample_image`) are executed UNMODIFIED twice -- once on the
+reference's own solver on CPU, once on dpm_solver_b200 -- with stub networks. Outputs must be bit-identical
+(classifier guidance on the GPU: <= 1e-5, the log_softmax gradient runs through the device's exp()).
+
+Two executors for the product arm: the numpy executor on CPU (host logic, `-m "not gpu"`) and CudaBackend on
+cuda:0 (`-m gpu`, the adapters run on the sm_100a kernels through the C-ABI). The reference bytecode comes from
+oracle/_ref (tests/adapters.py)."""
 import os
 import sys
-import types
 
 import numpy as np
 import pytest
 import torch
 
-REF = os.environ.get("DPM_REFERENCE", "/root/reference")
-ADAPTER_DIR = os.path.join(REF, "examples", "stable-diffusion", "ldm", "models", "diffusion", "dpm_solver")
-pytestmark = pytest.mark.skipif(not os.path.isdir(ADAPTER_DIR), reason="reference tree not available")
+import adapters as A
+from helpers import rel_err
+
+pytestmark = pytest.mark.skipif(not A.available(), reason="oracle/_ref not built and no reference tree")
+
+EXECUTORS = ["numpy-executor", pytest.param("cuda", marks=pytest.mark.gpu)]
 
 
-def load_adapter(pkg_name, solver_module):
-    """Import sampler.py inside a synthetic package whose `.dpm_solver` is `solver_module`."""
-    pkg = types.ModuleType(pkg_name)
-    pkg.__path__ = []
-    sys.modules[pkg_name] = pkg
-    sys.modules[pkg_name + ".dpm_solver"] = solver_module
-    spec = importlib.util.spec_from_file_location(pkg_name + ".sampler", os.path.join(ADAPTER_DIR, "sampler.py"))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[pkg_name + ".sampler"] = mod
-    spec.loader.exec_module(mod)
-    # the adapter pins its buffers to "cuda"; the acceptance run is on CPU
-    mod.DPMSolverSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
-    return mod
+@pytest.fixture(params=EXECUTORS)
+def product_device(request):
+    """Installs the executor for the product arm and yields the device its tensors live on."""
+    from dpm_solver_b200 import ops
+    old = ops._backend
+    if request.param == "cuda":
+        ops.set_backend(ops.CudaBackend())
+        yield "cuda:0"
+    else:
+        from oracle_backend import OracleBackend
+        ops.set_backend(OracleBackend())
+        yield "cpu"
+    ops.set_backend(old)
 
 
-class StubLatentDiffusion:
-    """What DPMSolverSampler touches: alphas_cumprod, betas.device, device, apply_model."""
-
-    def __init__(self):
-        betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
-        self.betas = betas.float()
-        self.alphas_cumprod = torch.cumprod(1 - betas, 0).float()
-        self.device = torch.device("cpu")
-        self.calls = []
-
-    def apply_model(self, x, t, c):
-        self.calls.append((float(t[0]), tuple(x.shape)))
-        return 0.1 * x + ((t * 0.001) * 0.05 - 0.02).reshape(-1, 1, 1, 1) + 0.05 * c.reshape(-1, 1, 1, 1)
-
-
-def vendored_solver():
-    spec = importlib.util.spec_from_file_location("_ref_sd_dpm_solver", os.path.join(ADAPTER_DIR, "dpm_solver.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+def _launches():
+    from dpm_solver_b200 import ops
+    be = ops.backend()
+    return be.launch_count() if hasattr(be, "launch_count") else 0
 
 
 @pytest.mark.parametrize("order,steps,method", [(2, 20, "multistep"), (3, 12, "multistep"), (2, 9, "singlestep")])
-def test_stable_diffusion_adapter_runs_unchanged(oracle_backend, order, steps, method):
+def test_stable_diffusion_adapter_runs_unchanged(product_device, order, steps, method):
     import dpm_solver_b200
-    ref_mod = load_adapter("_adapter_ref", vendored_solver())
-    new_mod = load_adapter("_adapter_b200", dpm_solver_b200)
     B, shape = 2, (4, 16, 16)
     x_T = torch.randn(B, *shape, generator=torch.Generator().manual_seed(3))
-    cond, uncond = torch.ones(B, 1), torch.zeros(B, 1)
     outs = []
-    for mod in (ref_mod, new_mod):
-        model = StubLatentDiffusion()
+    before = _launches()
+    for tag, solver, dev in (("ref", A.reference_solver("sd"), "cpu"), ("b200", dpm_solver_b200, product_device)):
+        mod = A.load_sd_adapter(solver, tag + product_device.replace(":", ""), dev)
+        model = A.StubLatentDiffusion(dev)
         sampler = mod.DPMSolverSampler(model)
         assert sampler.noise_schedule.total_N == 1000
-        x, inter = sampler.sample(S=steps, batch_size=B, shape=shape, conditioning=cond, x_T=x_T.clone(),
+        cond, uncond = torch.ones(B, 1, device=dev), torch.zeros(B, 1, device=dev)
+        x, inter = sampler.sample(S=steps, batch_size=B, shape=shape, conditioning=cond, x_T=x_T.clone().to(dev),
                                   unconditional_guidance_scale=7.5, unconditional_conditioning=uncond,
                                   order=order, method=method, verbose=False)
-        enc = sampler.stochastic_encode(x_T, 0.5, noise=torch.ones_like(x_T))
-        outs.append((x, inter, enc, model.calls))
-    (xr, ir, er, cr), (xn, in_, en, cn) = outs
-    assert cr == cn                                    # same network calls: doubled batch, same time labels
+        enc = sampler.stochastic_encode(x_T.to(dev), 0.5, noise=torch.ones_like(x_T).to(dev))
+        inv, _ = sampler.encode(S=10, x=x_T.to(dev), encode_ratio=0.6, conditioning=cond,
+                                unconditional_guidance_scale=3.0, unconditional_conditioning=uncond)
+        outs.append((x.cpu(), [i.cpu() for i in inter], enc.cpu(), inv.cpu(), model.calls))
+    (xr, ir, er, vr, cr), (xn, in_, en, vn, cn) = outs
+    if product_device != "cpu":
+        assert _launches() > before, "the CUDA library did not run"
+    assert [c[1] for c in cr] == [c[1] for c in cn]     # same network calls: doubled batch ...
+    np.testing.assert_allclose([c[0] for c in cn], [c[0] for c in cr], rtol=1e-6)   # ... same time labels
     np.testing.assert_array_equal(xn.numpy(), xr.numpy())
     assert len(ir) == len(in_)
     for a, b in zip(ir, in_):
         np.testing.assert_array_equal(b.numpy(), a.numpy())
     np.testing.assert_array_equal(en.numpy(), er.numpy())
+    np.testing.assert_array_equal(vn.numpy(), vr.numpy())
+
+
+def _sde_net(x, t):
+    return 0.1 * x + ((t * 0.05) - 0.02).reshape(-1, 1, 1, 1)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(denoise=True, steps=13), dict(algorithm_type="dpmsolver++", thresholding=True, order=2, steps=8),
+                                dict(skip_type="time_uniform", method="multistep", order=2, steps=12)])
+def test_score_sde_glue_runs_unchanged(product_device, kw):
+    """Continuous 'linear' VP schedule, singlestep order 3, logSNR grid, optional denoise / thresholding. The
+    example's own vendored (older) solver copy calls `correcting_x0_fn(x0)` with one argument and raises TypeError
+    with thresholding (examples/score_sde_pytorch/dpm_solver.py:449), so the current root file is the reference."""
+    import dpm_solver_b200
+    outs = []
+    for tag, solver, dev in (("ref", A.reference_solver("root"), "cpu"), ("b200", dpm_solver_b200, product_device)):
+        sampling = A.load_score_sde_sampling(solver, tag)
+        fn = sampling.get_dpm_solver_sampler(A.StubVPSDE(), (2, 3, 8, 8), lambda v: v, device=dev, **kw)
+        x, nfe = fn(_sde_net)
+        outs.append((x.cpu(), nfe))
+    assert outs[0][1] == outs[1][1]
+    np.testing.assert_array_equal(outs[1][0].numpy(), outs[0][0].numpy())
+
+
+@pytest.mark.parametrize("kw", [dict(),                                                       # classifier guidance + thresholding, ++3M
+                                dict(cond_class=False, thresholding=False, sample_type="dpmsolver", order=2, method="singlestep"),
+                                dict(denoise=True, timesteps=10, order=2),
+                                dict(thresholding=False, scale=0.5, fixed_class=None)])
+def test_guided_diffusion_runner_runs_unchanged(product_device, kw):
+    """`Diffusion.sample_image` (runners/diffusion.py:524-639): 6-channel network output split to the mean,
+    classifier guidance through autograd (:605-608, reference :315-321), dynamic thresholding, DDPM linear betas."""
+    import dpm_solver_b200
+    from cases import make_betas
+    betas = torch.from_numpy(make_betas("ddpm_linear")[1]).float()
+    x_T = torch.randn(3, 3, 16, 16, generator=torch.Generator().manual_seed(11))
+    use_classifier = kw.get("cond_class", True)
+    outs = []
+    for tag, solver, dev in (("ref", A.reference_solver("guided"), "cpu"), ("b200", dpm_solver_b200, product_device)):
+        _, sample_image = A.load_guided_runner(solver, tag)
+        me = A.guided_self(betas.to(dev), **kw)
+        torch.manual_seed(5)                      # the runner draws the class labels with the global generator (:534-536)
+        x, classes = sample_image(me, x_T.to(dev), A.guided_net, last=True,
+                                  classifier=A.guided_classifier if use_classifier else None)
+        outs.append((x.cpu(), None if classes is None else classes.cpu()))
+    (xr, cr), (xn, cn) = outs
+    if cr is not None:
+        assert torch.equal(cr, cn)
+    assert torch.isfinite(xr).all()
+    if product_device == "cpu" or not use_classifier:
+        np.testing.assert_array_equal(xn.numpy(), xr.numpy())
+    else:
+        assert rel_err(xn.numpy(), xr.numpy()) <= 1e-5
 
 
 def test_root_module_name_is_a_drop_in():

@@ -1,11 +1,9 @@
 """Reference-rounding mode (dpm_step_desc.raw_round, DPM_Solver(reference_rounding=True)) on the GPU: the
 generic kernel's <RND> instantiation against the numpy executor, bit for bit, and one sample() run.
 
-STAGED: the semantics are pinned on CPU against the unmodified reference
-(tests/test_random_configs_vs_reference.py::test_reference_rounding_mode_is_bit_identical); the CUDA
-instantiation was written after this round's GPU budget was spent (the default kernels are unchanged, SASS
-compared), so until it has run on a B200 the tests are non-strict xfail: a pass shows as XPASS, a failure
-does not turn the suite red. Remove the mark once it has passed on hardware."""
+The semantics are pinned on CPU against the unmodified reference
+(tests/test_random_configs_vs_reference.py::test_reference_rounding_mode_is_bit_identical); all cases passed on
+a B200 in round 1's driver run (39 XPASS), so the tests are strict now."""
 import random
 
 import pytest
@@ -15,7 +13,7 @@ from dpm_solver_b200._lib import (FORM_DIFF2, FORM_LIN1, FORM_LIN3, FORM_MS3, FO
 from dpm_solver_b200.ops import StepArgs
 from oracle_backend import OracleBackend
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="reference_rounding kernels not yet run on B200 (staged)", strict=False)]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

@@ -42,11 +42,17 @@ def test_known_answers_config1(golden, cuda_backend):
     assert np.allclose(y[0, 0, 0, :3].cpu().numpy(), ref, rtol=1e-5)
 
 
+# max|y - y_ref| / max|y_ref| of 16-bit storage (state AND network output) against the fp32 reference golden,
+# measured with the numpy executor (which the CUDA path reproduces bit for bit): (bf16, f16)
+MEASURED_16 = {"pp2m": (1.598e-2, 2.764e-3), "pp3m": (5.049e-2, 5.204e-3), "eps3s_cfg": (5.927e-3, 1.425e-3),
+               "pp3m_thr": (5.929e-2, 6.187e-3), "pp2m_cfg_v": (2.751e-2, 2.979e-3), "pp3s_taylor": (1.541e-2, 1.825e-3)}
+
+
 @pytest.mark.parametrize("name", ["pp2m", "pp3m", "eps3s_cfg", "pp3m_thr", "pp2m_cfg_v", "pp3s_taylor"])
 @pytest.mark.parametrize("sdt", [torch.bfloat16, torch.float16])
 def test_sample_16bit_state(golden, cuda_backend, oracle_backend_cpu, name, sdt):
     """16-bit storage (fp32 math, RN on store): bitwise equal to the numpy executor run with the
-    same storage type, and within storage precision of the fp32 reference."""
+    same storage type, and within 1.5x the MEASURED storage-precision deviation from the fp32 reference."""
     from dpm_solver_b200 import ops
     case = CASES[name]
     y, _, _ = run_product_case(case, device="cuda:0", state_dtype=sdt, model_dtype=sdt)
@@ -56,8 +62,8 @@ def test_sample_16bit_state(golden, cuda_backend, oracle_backend_cpu, name, sdt)
     if not case.get("thresholding"):
         assert torch.equal(y.cpu(), y_ref)
     g = golden["samples"][f"{name}/y"]
-    eps = 2 ** -8 if sdt == torch.bfloat16 else 2 ** -11
-    assert rel_err(y.float().cpu().numpy(), g) < 40 * eps
+    measured = MEASURED_16[name][0 if sdt == torch.bfloat16 else 1]
+    assert rel_err(y.float().cpu().numpy(), g) <= 1.5 * measured      # (the full-size bound: test_vs_reference_workloads.py)
 
 
 def test_mixed_bf16_model_fp32_state(golden, cuda_backend):

@@ -1,4 +1,4 @@
-"""Randomised end-to-end parity against the UNMODIFIED reference (build container only).
+"""Randomised end-to-end parity against the UNMODIFIED reference (oracle/_ref).
 
 Draws sampling configurations at random (schedule, algorithm, method, order, steps, skip type,
 solver type, parameterisation, CFG, thresholding, t_end, denoise_to_zero), runs the reference on CPU
@@ -13,20 +13,17 @@ import numpy as np
 import pytest
 import torch
 
-REF = os.environ.get("DPM_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "dpm_solver_pytorch.py")),
-                                reason="reference tree not available")
+from oracle import ref_loader  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not built and no reference tree")
 
 from cases import exact_net, make_betas, seeded  # noqa: E402
 
 
 def reference_module():
-    import importlib.util
+    """The unmodified reference (oracle/_ref bytecode of /root/reference/dpm_solver_pytorch.py)."""
     warnings.filterwarnings("ignore")
-    spec = importlib.util.spec_from_file_location("_ref_dpm_solver_pytorch", os.path.join(REF, "dpm_solver_pytorch.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    return ref_loader.load("dpm_solver_pytorch")
 
 
 def draw(rng):
