@@ -17,8 +17,13 @@ metric = solver-update GElem/s = elements(x) * updates / seconds, whole job over
   cpu_baseline : the reference algorithm on the host cores (oracle, torch-CPU namespace: the same
               chain of ATen elementwise ops and sort-based interpolation the reference executes)
 
---impl reference runs only that CPU arm (the unmodified reference is a Python file that does not
-exist on the GPU box; oracle/dpm_oracle.py is its op-for-op restatement, pinned by tests/golden).
+  workloads : (default N=1 run) the other single-GPU BASELINE configs, c3 and c4, each with value / roofline / clocks
+  parity    : outside the timed region, a batch slice of the run's own output is compared with the UNMODIFIED
+              reference (oracle/_ref, CPU fp32) on the same inputs -> config.parity_checked
+
+--impl reference runs the UNMODIFIED reference (oracle/_ref: /root/reference/dpm_solver_pytorch.py byte-compiled by
+oracle/build_ref.py, shipped to the box) on the host cores; the oracle port is only the fallback when that
+bytecode is missing (cpu_baseline.kind says which).
 """
 import argparse
 import json
@@ -180,14 +185,30 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(w, sample_batch, repeats=1, warmup=0):
-    """Time the oracle (torch-CPU namespace) on a bounded sample of the workload; returns
-    (GElem/s, seconds per sample() call, cores)."""
+def host_cores():
+    return os.cpu_count() or 1
+
+
+def _reference_once(w, sample_batch):
+    """Closure running one sample() of the UNMODIFIED reference (oracle/_ref) on CPU, or None if unavailable."""
+    try:
+        import refcheck as R
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return None
+        ref = ref_loader.load("dpm_solver_pytorch")
+    except Exception:
+        return None
+    x, banks = R.synthetic(w, sample_batch, "cpu", torch.float32, nbanks=2)
+    solver, _ = R._solver(ref, w, banks, "cpu")
+    kw = R.sample_kwargs(w)
+    return lambda: solver.sample(x, **kw)
+
+
+def _port_once(w, sample_batch):
     from cases import make_betas
     from oracle import dpm_oracle as O
     TH = O.torch_namespace()
-    cores = usable_cores()
-    torch.set_num_threads(cores)
     kind, betas = make_betas(w["schedule"])
     ns = O.VPSchedule.from_betas(betas, xp=TH) if kind == "discrete" else O.VPSchedule("linear", xp=TH)
     shape = (sample_batch,) + tuple(w["shape"][1:])
@@ -203,15 +224,22 @@ def cpu_arm(w, sample_batch, repeats=1, warmup=0):
 
     smp = O.Sampler(ns, net, algorithm_type=w["algo"], guidance_scale=w["cfg"],
                     thresholding=(0.995, 1.0) if w["thresholding"] else None)
+    if w["method"] == "multistep":
+        return lambda: smp.multistep(x, w["steps"], w["order"])
+    return lambda: smp.singlestep(x, w["steps"], w["order"])
 
-    def once():
-        if w["method"] == "multistep":
-            return smp.multistep(x, w["steps"], w["order"])
-        return smp.singlestep(x, w["steps"], w["order"])
 
+def cpu_arm(w, sample_batch, repeats=1, warmup=0):
+    """Time the reference's own CPU implementation on a bounded sample of the workload: the unmodified reference
+    from oracle/_ref (kind "reference"), else the oracle port in its torch-CPU namespace (kind "port").
+    Returns (GElem/s, seconds per sample() call, threads used, kind)."""
+    once, kind = _reference_once(w, sample_batch), "reference"
+    if once is None:
+        once, kind = _port_once(w, sample_batch), "port"
+    cores = usable_cores()
     with torch.no_grad():
         # "all the host threads it can use": on many-core hosts the reference's small scalar ops and
-        # 1M-element tensors run slower with every core than with a few, so take the fastest setting
+        # MB-sized tensors run slower with every core than with a few, so take the fastest setting
         best = None
         for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
             torch.set_num_threads(nt)
@@ -221,45 +249,64 @@ def cpu_arm(w, sample_batch, repeats=1, warmup=0):
             dt1 = time.perf_counter() - t0
             if best is None or dt1 < best[0]:
                 best = (dt1, nt)
-        cores = best[1]
-        torch.set_num_threads(cores)
+        threads = best[1]
+        torch.set_num_threads(threads)
         for _ in range(warmup):
             once()
         t0 = time.perf_counter()
         for _ in range(repeats):
             once()
         dt = (time.perf_counter() - t0) / repeats
-    E = int(np.prod(shape))
-    return E * n_updates(w) / dt / 1e9, dt, cores
+    E = sample_batch * int(np.prod(w["shape"][1:]))
+    return E * n_updates(w) / dt / 1e9, dt, threads, kind
+
+
+def cpu_sample_batch(w):
+    """Bounded sample of the per-GPU batch for the CPU arms: 8.4 M (latents) / 3.1 M (pixels) elements per tensor --
+    33 / 12.6 MB fp32, beyond the per-core caches, about a second per sample() call."""
+    return 512 if w["shape"][-1] <= 64 else 16
 
 
 def eager_cuda_arm(w, dev, repeats=3):
-    """The reference algorithm as stock eager PyTorch CUDA ops on the same GPU (oracle, torch namespace
-    on the device): per update 3/7/16 full-tensor launches plus ~40 tiny launches per schedule scalar.
-    fp32 state (the reference promotes every update to fp32). Returns (GElem/s, ms per sample())."""
-    from cases import make_betas
-    from oracle import dpm_oracle as O
-    TH = O.torch_namespace(dev)
-    kind, betas = make_betas(w["schedule"])
-    ns = O.VPSchedule.from_betas(betas, xp=TH) if kind == "discrete" else O.VPSchedule("linear", xp=TH)
+    """The second, fairer baseline: the UNMODIFIED reference (oracle/_ref) run as stock eager PyTorch CUDA ops on the
+    same GPU -- per update 3/7/16 full-tensor launches plus ~40 tiny launches per schedule scalar; fp32 state (the
+    reference promotes every update to fp32). Full workload shape, or the largest batch torch.quantile accepts
+    (16 M elements) when thresholding is on. Falls back to the oracle port's torch namespace when oracle/_ref is
+    missing. Returns (GElem/s, ms per sample(), kind)."""
+    import refcheck as R
+    from oracle import ref_loader
     shape = tuple(w["shape"])
-    g = torch.Generator(device=dev).manual_seed(1234)
-    x = torch.randn(shape, device=dev, generator=g)
-    nb = 2 if w["cfg"] else 1
-    banks = [torch.randn((nb * shape[0],) + shape[1:], device=dev, generator=g) for _ in range(2)]
-    cnt = [0]
-
-    def net(xx, tt):
-        cnt[0] += 1
-        return banks[cnt[0] % 2]
-
-    smp = O.Sampler(ns, net, algorithm_type=w["algo"], guidance_scale=w["cfg"],
-                    thresholding=(0.995, 1.0) if w["thresholding"] else None)
-    smp.log_calls = False
     if w["thresholding"]:
-        return None   # the oracle's quantile is a numpy sort: not an eager-CUDA path
-    once = (lambda: smp.multistep(x, w["steps"], w["order"])) if w["method"] == "multistep" else \
-        (lambda: smp.singlestep(x, w["steps"], w["order"]))
+        shape = (min(shape[0], (1 << 24) // int(np.prod(shape[1:])) - 1),) + shape[1:]
+    if ref_loader.available():
+        kind = "reference"
+        x, banks = R.synthetic(w, shape[0], dev, torch.float32, nbanks=2)
+        solver, _ = R._solver(ref_loader.load("dpm_solver_pytorch"), w, banks, dev)
+        kw = R.sample_kwargs(w)
+        once = lambda: solver.sample(x, **kw)
+    else:
+        kind = "port"
+        if w["thresholding"]:
+            return None   # the oracle's quantile is a numpy sort: not an eager-CUDA path
+        from cases import make_betas
+        from oracle import dpm_oracle as O
+        TH = O.torch_namespace(dev)
+        k2, betas = make_betas(w["schedule"])
+        ns = O.VPSchedule.from_betas(betas, xp=TH) if k2 == "discrete" else O.VPSchedule("linear", xp=TH)
+        g = torch.Generator(device=dev).manual_seed(1234)
+        x = torch.randn(shape, device=dev, generator=g)
+        nb = 2 if w["cfg"] else 1
+        banks = [torch.randn((nb * shape[0],) + shape[1:], device=dev, generator=g) for _ in range(2)]
+        cnt = [0]
+
+        def net(xx, tt):
+            cnt[0] += 1
+            return banks[cnt[0] % 2]
+
+        smp = O.Sampler(ns, net, algorithm_type=w["algo"], guidance_scale=w["cfg"], thresholding=None)
+        smp.log_calls = False
+        once = (lambda: smp.multistep(x, w["steps"], w["order"])) if w["method"] == "multistep" else \
+            (lambda: smp.singlestep(x, w["steps"], w["order"]))
     with torch.no_grad():
         once()
         torch.cuda.synchronize()
@@ -270,21 +317,23 @@ def eager_cuda_arm(w, dev, repeats=3):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / repeats
-    return int(np.prod(shape)) * n_updates(w) / (ms * 1e-3) / 1e9, ms
+    return int(np.prod(shape)) * n_updates(w) / (ms * 1e-3) / 1e9, ms, kind
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = 64 if w["shape"][-1] <= 64 else 4
-    val, dt, cores = cpu_arm(w, sample_batch, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    sample_batch = cpu_sample_batch(w)
+    val, dt, cores, kind = cpu_arm(w, sample_batch, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
     out = {
         "impl": "reference", "metric": "solver-update GElem/s", "value": val, "unit": "GElem/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "sample": f"batch {sample_batch} of the per-GPU batch, fp32 on CPU"},
-        "cpu_baseline": {"value": val, "unit": "GElem/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "GElem/s", "cores": cores, "threads": cores, "host_cores": host_cores(),
+                         "usable_cores": usable_cores(), "kind": kind,
+                         "what": "unmodified dpm_solver_pytorch.py (oracle/_ref bytecode) on CPU tensors" if kind == "reference" else "oracle port, torch-CPU namespace",
                          "sample": f"[{sample_batch},{','.join(map(str, w['shape'][1:]))}] fp32, {w['steps']} solver steps per sample() call"},
         "e2e": {"value": val, "unit": "GElem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -389,35 +438,89 @@ def headline_kernels(be, peak, shape=(4096, 4, 64, 64), reps=50):
     return out
 
 
-def run_b200(args, w):
-    import torch.distributed as dist
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and with the default first-touch policy its pinned host buffers) to the CPUs NVML reports
+    as local to GPU `local`, BEFORE anything is allocated: with 8 ranks each moving 2 x 134 MB per step through
+    pinned memory, buffers on the wrong socket cross the inter-socket link twice. Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].strip().isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"bound": False, "why": "no overlap between the GPU's CPU affinity and this process's cpuset"}
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            for n in sorted(os.listdir("/sys/devices/system/node")):
+                if n.startswith("node") and n[4:].isdigit():
+                    lst = open(f"/sys/devices/system/node/{n}/cpulist").read().strip()
+                    ids = set()
+                    for part in lst.split(","):
+                        lo, _, hi = part.partition("-")
+                        ids.update(range(int(lo), int(hi or lo) + 1))
+                    if min(cpus) in ids:
+                        node = int(n[4:])
+        except Exception:
+            pass
+        return {"bound": True, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:
+        return {"bound": False, "why": repr(e)[:120]}
+
+
+class Ctx:
+    """Per-process state shared by the workloads of one bench run."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
+        self.numa = bind_to_gpu_numa_node(self.local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL's own environment (NCCL_DEBUG, ...) is left exactly as the launcher set it
+            dist.init_process_group("nccl", device_id=self.dev)
+        from dpm_solver_b200 import ops
+        self.be = make_timed_backend()
+        ops.set_backend(self.be)
+        self.be.set_tuning(args.variant, args.threads, args.ctas)
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def build_solver(ctx, w, B, seed, inputs=None):
+    """Synthetic inputs (or the given (x_T, banks)) + the product solver for a B-sample batch of workload `w` on
+    this rank's GPU."""
     from cases import make_betas
-    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper, ops
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DPM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    be = make_timed_backend()
-    ops.set_backend(be)
-    be.set_tuning(args.variant, args.threads, args.ctas)
-
-    dt = DT[w["dtype"]]
-    shape = tuple(w["shape"])
-    B = shape[0]
-    E = int(np.prod(shape))
+    from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper
+    import refcheck as R
+    dev, dt = ctx.dev, DT[w["dtype"]]
     kind, betas = make_betas(w["schedule"])
     ns = NoiseScheduleVP("discrete", betas=torch.from_numpy(betas)) if kind == "discrete" else NoiseScheduleVP("linear")
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x_T = torch.randn(shape, device=dev, generator=g).to(dt)
-    nb = 2 if w["cfg"] else 1
-    banks = [torch.randn((nb * B,) + shape[1:], device=dev, generator=g).to(dt) for _ in range(3)]
+    x_T, banks = inputs if inputs is not None else R.synthetic(w, B, dev, dt, seed=seed)
     cnt = [0]
     if w["cfg"]:
         def net(xx, tt, cc):
@@ -432,146 +535,246 @@ def run_b200(args, w):
         fn = model_wrapper(net, ns)
     solver = DPM_Solver(fn, ns, algorithm_type=w["algo"], state_dtype=dt,
                         correcting_x0_fn="dynamic_thresholding" if w["thresholding"] else None,
-                        plan_broadcast=world > 1)
+                        plan_broadcast=ctx.world > 1)
     kw = dict(steps=w["steps"], order=w["order"], method=w["method"], skip_type="time_uniform")
+    return solver, kw, x_T, banks, cnt
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+# measured storage-precision deviation of 16-bit state from the fp32 reference (tests/test_vs_reference_workloads.py)
+PARITY_BOUND_16 = {("c2", "bf16"): (2.30e-2, 1.07e-2), ("c3", "bf16"): (9.84e-3, 4.07e-3), ("c4", "bf16"): (2.34e-2, 5.48e-3)}
+
+
+def parity_check(name, w, solver, kw, x_T, banks, cnt):
+    """Outside the timed region: the run's own configuration, one more sample() with the bank rotation reset, a batch
+    slice of its output against the UNMODIFIED reference (oracle/_ref, CPU fp32) on the same rows of the inputs."""
+    try:
+        import refcheck as R
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return {"parity_checked": False, "why": "oracle/_ref not built"}
+        B = x_T.shape[0]
+        rows = 8 if w["shape"][-1] <= 64 else 2
+        cnt[0] = 0
+        y = solver.sample(x_T, **kw)
+        torch.cuda.synchronize()
+        xs = x_T[:rows].cpu()
+        bs = [R.slice_rows(b, B, rows, w["cfg"]).cpu() for b in banks]
+        yr = R.reference_sample(w, xs, bs, device="cpu")
+        got = y[:rows].float().cpu()
+        mx, rms = R.rel_err(got.numpy(), yr.numpy()), R.rms_rel_err(got.numpy(), yr.numpy())
+        out = {"rows": rows, "max_rel_err": mx, "rms_rel_err": rms, "reference": "unmodified dpm_solver_pytorch.py (oracle/_ref), CPU fp32",
+               "reference_absmean": float(yr.abs().mean()), "absmean": float(got.abs().mean())}
+        if w["dtype"] == "f32":
+            out["bit_exact"] = bool(torch.equal(got, yr))
+            out["parity_checked"] = out["bit_exact"]
+        else:
+            bmx, brms = PARITY_BOUND_16.get((name, w["dtype"]), (5e-2, 2e-2))
+            out["bound"] = {"max_rel_err": 1.5 * bmx, "rms_rel_err": 1.5 * brms, "what": "1.5 x the measured bf16-storage deviation"}
+            out["parity_checked"] = bool(mx <= 1.5 * bmx and rms <= 1.5 * brms)
+        return out
+    except Exception as e:
+        return {"parity_checked": False, "why": repr(e)[:200]}
+
+
+def shard_parity(ctx, w):
+    """T6 inside the bench: a small global batch (same seed on every rank), split over the ranks, must equal rank 0's
+    single-GPU run of the whole batch bit for bit (concatenated shards == unsharded); shards meet by all_gather."""
+    import refcheck as R
+    dist = ctx.dist
+    per = 16 if w["shape"][-1] <= 64 else 2
+    Bg = per * ctx.world
+    x_g, banks_g = R.synthetic(w, Bg, ctx.dev, DT[w["dtype"]], seed=4321)
+    lo, hi = ctx.rank * per, (ctx.rank + 1) * per
+    x_s = x_g[lo:hi].contiguous()
+    banks_s = [(torch.cat([b[lo:hi], b[Bg + lo:Bg + hi]]) if w["cfg"] else b[lo:hi]).contiguous() for b in banks_g]
+    solver_s, kw, _, _, _ = build_solver(ctx, w, per, 0, inputs=(x_s, banks_s))
+    y_s = solver_s.sample(x_s, **kw).contiguous()
+    gathered = [torch.empty_like(y_s) for _ in range(ctx.world)]
+    dist.all_gather(gathered, y_s)
+    ok = True
+    if ctx.rank == 0:
+        solver_g, _, _, _, _ = build_solver(ctx, w, Bg, 0, inputs=(x_g, banks_g))
+        ok = bool(torch.equal(torch.cat(gathered), solver_g.sample(x_g, **kw)))
+    flag = torch.tensor([1 if ok else 0], device=ctx.dev)
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
+def measure(ctx, args, name, w, steps, warmup, with_e2e=True):
+    """Time one workload on this process's GPU; returns the dict of a bench line (rank 0) or None."""
+    be, dev, world, rank = ctx.be, ctx.dev, ctx.world, ctx.rank
+    dt = DT[w["dtype"]]
+    shape = tuple(w["shape"])
+    B = shape[0]
+    E = int(np.prod(shape))
+    solver, kw, x_T, banks, cnt = build_solver(ctx, w, B, seed=1234 + rank)
 
     # ---- warm-up ----
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         y = solver.sample(x_T, **kw)
-    barrier()
+    ctx.barrier()
 
     # ---- timed region: inputs resident in HBM ----
     launches0 = be.launch_count()
     be.recording, be.records = True, []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
+    with ClockSampler(ctx.local) as clk:
+        ctx.barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             y = solver.sample(x_T, **kw)
         e1.record()
-        barrier()
+        ctx.barrier()
     be.recording = False
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = be.launch_count() - launches0
     ksum = be.summary()
     if os.environ.get("DPM_BENCH_TRACE") and rank == 0:
-        for key, b, a0, a1 in be.records[:2 * w["steps"] + 2]:
-            print(f"trace {key:40s} {a0.elapsed_time(a1) * 1e3:8.1f} us  gap_to_next", file=sys.stderr)
         recs = be.records
+        for key, b, a0, a1 in recs[:2 * w["steps"] + 2]:
+            print(f"trace {key:40s} {a0.elapsed_time(a1) * 1e3:8.1f} us", file=sys.stderr)
         for i in range(min(len(recs) - 1, 2 * w["steps"])):
             print(f"gap {i}: {recs[i][3].elapsed_time(recs[i + 1][2]) * 1e3:7.1f} us", file=sys.stderr)
-    value = world * E * n_updates(w) * args.steps / (ms * 1e-3) / 1e9
+    value = world * E * n_updates(w) * steps / (ms * 1e-3) / 1e9
 
-    # ---- e2e: host buffers; every step copies its x_T host->device (pinned) and its result
-    # device->host inside the timed region. Software-pipelined over three streams (copy-in, compute,
-    # copy-out) with double buffers, the way a serving loop would feed the public API.
-    n_buf = 2
-    x_host = [x_T.cpu().pin_memory() for _ in range(n_buf)]
-    y_host = [torch.empty_like(x_host[0]).pin_memory() for _ in range(n_buf)]
-    x_dev = [torch.empty_like(x_T) for _ in range(n_buf)]
-    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    e2e = None
+    if with_e2e:
+        # ---- e2e: host buffers; every step copies its x_T host->device (pinned) and its result device->host inside
+        # the timed region. Software-pipelined over three streams (copy-in, compute, copy-out) with double buffers,
+        # the way a serving loop would feed the public API.
+        n_buf = 2
+        x_host = [x_T.cpu().pin_memory() for _ in range(n_buf)]
+        y_host = [torch.empty_like(x_host[0]).pin_memory() for _ in range(n_buf)]
+        x_dev = [torch.empty_like(x_T) for _ in range(n_buf)]
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_loop(n_steps):
-        ev_in = [None] * n_buf      # copy-in of buffer b finished
-        ev_cmp = [None] * n_buf     # compute that read x_dev[b] finished
-        ev_out = [None] * n_buf     # copy-out into y_host[b] finished
-        ys = [None] * n_buf
-        for i in range(n_steps):
-            b = i % n_buf
-            with torch.cuda.stream(s_in):
-                if ev_cmp[b] is not None:
-                    s_in.wait_event(ev_cmp[b])               # x_dev[b] no longer read
-                x_dev[b].copy_(x_host[b], non_blocking=True)
-                ev_in[b] = torch.cuda.Event(); ev_in[b].record(s_in)
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_in[b])
-                if ev_out[b] is not None:
-                    s_cmp.wait_event(ev_out[b])              # previous result of this slot has left
-                ys[b] = solver.sample(x_dev[b], **kw)
-                ev_cmp[b] = torch.cuda.Event(); ev_cmp[b].record(s_cmp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[b])
-                y_host[b].copy_(ys[b], non_blocking=True)
-                ev_out[b] = torch.cuda.Event(); ev_out[b].record(s_out)
-        for st in (s_in, s_cmp, s_out):
-            torch.cuda.current_stream().wait_stream(st)
+        def e2e_loop(n_steps):
+            ev_in = [None] * n_buf      # copy-in of buffer b finished
+            ev_cmp = [None] * n_buf     # compute that read x_dev[b] finished
+            ev_out = [None] * n_buf     # copy-out into y_host[b] finished
+            ys = [None] * n_buf
+            for i in range(n_steps):
+                b = i % n_buf
+                with torch.cuda.stream(s_in):
+                    if ev_cmp[b] is not None:
+                        s_in.wait_event(ev_cmp[b])               # x_dev[b] no longer read
+                    x_dev[b].copy_(x_host[b], non_blocking=True)
+                    ev_in[b] = torch.cuda.Event(); ev_in[b].record(s_in)
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[b])
+                    if ev_out[b] is not None:
+                        s_cmp.wait_event(ev_out[b])              # previous result of this slot has left
+                    ys[b] = solver.sample(x_dev[b], **kw)
+                    ev_cmp[b] = torch.cuda.Event(); ev_cmp[b].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[b])
+                    y_host[b].copy_(ys[b], non_blocking=True)
+                    ev_out[b] = torch.cuda.Event(); ev_out[b].record(s_out)
+            for st in (s_in, s_cmp, s_out):
+                torch.cuda.current_stream().wait_stream(st)
 
-    e2e_loop(2)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk2:
-        e2.record()
-        e2e_loop(args.steps)
-        e3.record()
-        barrier()
-    clk.rows += clk2.rows
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
-    e2e_val = world * E * n_updates(w) * args.steps / (ms_e2e * 1e-3) / 1e9
-    checksum = float(y_host[(args.steps - 1) % n_buf].float().abs().mean())
-    x_host, y_host = x_host[0], y_host[0]
+        e2e_loop(2)
+        ctx.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(ctx.local) as clk2:
+            e2.record()
+            e2e_loop(steps)
+            e3.record()
+            ctx.barrier()
+        clk.rows += clk2.rows
+        ms_e2e_rank = e2.elapsed_time(e3)
+        ms_e2e = ctx.max_over_ranks(ms_e2e_rank)
+        h2d = x_host[0].numel() * x_host[0].element_size()
+        d2h = y_host[0].numel() * y_host[0].element_size()
+        checksum = float(y_host[(steps - 1) % n_buf].float().abs().mean())
+        e2e = {"value": world * E * n_updates(w) * steps / (ms_e2e * 1e-3) / 1e9, "unit": "GElem/s",
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / steps,
+               # what bounds it: each rank moves h2d + d2h bytes per step over its PCIe link, concurrently in both directions
+               "pcie_gbs_per_rank_each_direction": h2d / (ms_e2e / steps * 1e-3) / 1e9,
+               "limiter": "PCIe: one x_T in and one x_0 out per sample() per rank, full duplex; the device-side step takes %.2f ms" % (ms / steps),
+               "numa": ctx.numa, "checksum_absmean": checksum}
+        del x_host, y_host, x_dev
 
-    if rank == 0:
-        peak, peak_src = hbm_peak()
-        dom_key = max(ksum, key=lambda k: ksum[k]["ms"])
-        dom = ksum[dom_key]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
+    par = parity_check(name, w, solver, kw, x_T, banks, cnt) if rank == 0 else None
+    if rank != 0:
+        return None
+    peak, peak_src = hbm_peak()
+    dom_key = max(ksum, key=lambda k: ksum[k]["ms"])
+    dom = ksum[dom_key]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get(name, {}).get(dom_key)
+            traffic_src = tj.get("_source", "profiles/roofline_traffic.json") + " (static: one ncu --set full capture of this kernel, not measured by this run)"
+        except Exception:
+            traffic = None
+    out = {
+        "metric": "solver-update GElem/s", "value": value, "unit": "GElem/s", "n_gpus": world, "steps": steps,
+        "warmup": max(warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["desc"], "per_gpu_shape": list(shape), "global_batch": B * world,
+                   "parallelism": f"batch-sharded x{world}, one broadcast of the scalar plan, no tensor traffic",
+                   "l2": "per-update working set (x, eps bank, buffers: >= 4 x %.0f MB) exceeds the 126 MB L2; eps banks rotate" % (E * x_T.element_size() / 1e6),
+                   "variant": args.variant, "parity_checked": bool(par and par.get("parity_checked"))},
+        "parity": par,
+        "hbm_gbs_total": sum(d["bytes"] for d in ksum.values()) / (sum(d["ms"] for d in ksum.values()) * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": dom["gbs"] / peak, "peak_source": peak_src, "bytes_per_launch": dom["bytes_per_launch"],
+                     "avg_us": dom["avg_us"], "launches": dom["launches"], "traffic": traffic, "traffic_source": traffic_src},
+        "kernels": ksum,
+        "gpu_launches": gpu_launches,
+        "clocks": clk.summary(),
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    del y, banks, x_T, solver
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_b200(args, w):
+    ctx = Ctx(args)
+    out = measure(ctx, args, args.workload, w, args.steps, args.warmup)
+    if ctx.world > 1:
+        ok = shard_parity(ctx, w)
+        if ctx.rank == 0:
+            out["config"]["shard_parity"] = ok
+    if ctx.rank == 0:
+        if not args.no_extras:
+            # the other single-GPU BASELINE configs, driver-visible in the same line (value, roofline, clocks each)
+            others = {}
+            for name in ("c3", "c4"):
+                if name == args.workload or ctx.world > 1:
+                    continue
+                try:
+                    o = measure(ctx, args, name, WORKLOADS[name], max(2, min(args.steps, 5)), 3, with_e2e=False)
+                    others[name] = {k: o[k] for k in ("value", "unit", "ms_per_step", "steps", "dtype", "config", "parity", "roofline",
+                                                        "hbm_gbs_total", "kernels", "gpu_launches", "clocks")}
+                except Exception as e:   # never let an extra leg break the headline
+                    others[name] = {"error": repr(e)[:200]}
+            if others:
+                out["workloads"] = others
+        if ctx.world == 1 and not args.no_extras:
+            peak, _ = hbm_peak()
+            out["kernels_alone"] = headline_kernels(ctx.be, peak)
+            sample_batch = cpu_sample_batch(w)
+            val, dtc, threads, kind = cpu_arm(w, sample_batch, repeats=1, warmup=0)
+            out["cpu_baseline"] = {"value": val, "unit": "GElem/s", "cores": threads, "threads": threads, "host_cores": host_cores(),
+                                   "usable_cores": usable_cores(), "kind": kind,
+                                   "sample": f"[{sample_batch},{','.join(map(str, w['shape'][1:]))}] fp32, {w['steps']} solver steps, {dtc * 1e3:.0f} ms"}
             try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom_key)
-            except Exception:
-                traffic = None
-        out = {
-            "metric": "solver-update GElem/s", "value": value, "unit": "GElem/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-            "config": {"workload": w["desc"], "per_gpu_shape": list(shape), "global_batch": B * world,
-                       "parallelism": f"batch-sharded x{world}, one broadcast of the scalar plan, no tensor traffic",
-                       "l2": "per-update working set (x, eps bank, buffers: >= 4 x %.0f MB) exceeds the 126 MB L2; eps banks rotate" % (E * x_T.element_size() / 1e6),
-                       "variant": args.variant, "checksum_absmean": checksum},
-            "hbm_gbs_total": sum(d["bytes"] for d in ksum.values()) / (sum(d["ms"] for d in ksum.values()) * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["gbs"] / peak, "peak_source": peak_src, "bytes_per_launch": dom["bytes_per_launch"],
-                         "avg_us": dom["avg_us"], "launches": dom["launches"], "traffic": traffic},
-            "kernels": ksum,
-            "e2e": {"value": e2e_val, "unit": "GElem/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size() * world,
-                    "d2h_bytes_per_step": y_host.numel() * y_host.element_size() * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": gpu_launches,
-            "clocks": clk.summary(),
-        }
-        if world == 1 and not args.no_extras:
-            del y, banks
-            torch.cuda.empty_cache()
-            out["kernels_alone"] = headline_kernels(be, peak)
-            sample_batch = 64 if shape[-1] <= 64 else 4
-            val, dtc, cores = cpu_arm(w, sample_batch, repeats=1, warmup=1)
-            out["cpu_baseline"] = {"value": val, "unit": "GElem/s", "cores": cores, "kind": "port",
-                                   "sample": f"[{sample_batch},{','.join(map(str, shape[1:]))}] fp32, {w['steps']} solver steps, {dtc * 1e3:.0f} ms"}
-            try:
-                eg = eager_cuda_arm(w, dev)
+                eg = eager_cuda_arm(w, ctx.dev)
                 if eg is not None:
-                    out["eager_cuda_baseline"] = {"value": eg[0], "unit": "GElem/s", "ms_per_step": eg[1], "dtype": "f32",
-                                                  "what": "the reference algorithm as stock eager PyTorch CUDA kernels on the same GPU (oracle port, torch namespace on cuda), full workload shape"}
+                    out["eager_cuda_baseline"] = {"value": eg[0], "unit": "GElem/s", "ms_per_step": eg[1], "dtype": "f32", "kind": eg[2],
+                                                  "what": "the reference algorithm as stock eager PyTorch CUDA kernels on the same GPU, full workload shape"}
             except Exception as e:   # never let the extra leg break the bench line
                 out["eager_cuda_baseline"] = {"error": repr(e)[:200]}
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -584,7 +787,8 @@ def main():
     ap.add_argument("--variant", type=int, default=2, help="0 direct, 1 TMA ring, 2 auto")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
-    ap.add_argument("--no-extras", action="store_true", help="skip the kernel-alone and CPU-baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3/c4, kernel-alone and CPU-baseline legs")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kEThreads) k_err_partial(const __grid_constant
   const int tid = threadIdx.x;
   float acc = 0.f;
   auto term = [&](float h, float l, float q) {
-    const float delta = fmaxf(p.atol, p.rtol * fmaxf(fabsf(l), fabsf(q)));   // :999
+    const float delta = max_nan(p.atol, p.rtol * max_nan(fabsf(l), fabsf(q)));   // :999
     const float v = (h - l) / delta;                                           // :1001
     acc += v * v;
   };
@@ -95,12 +95,12 @@ __global__ void __launch_bounds__(kEThreads) k_err_final(const __grid_constant__
     double s = 0.0;
     for (uint32_t c = 0; c < p.chunks; ++c) s += (double)p.partial[b * p.chunks + c];
     const float e = sqrtf((float)(s / (double)p.per_sample));   // norm_fn :1000
-    mx = fmaxf(mx, e);
+    mx = max_nan(mx, e);   // a NaN error norm must reach the controller (reference: torch .max())
   }
   best[threadIdx.x] = mx;
   __syncthreads();
   for (int o = kEThreads / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) best[threadIdx.x] = fmaxf(best[threadIdx.x], best[threadIdx.x + o]);
+    if (threadIdx.x < o) best[threadIdx.x] = max_nan(best[threadIdx.x], best[threadIdx.x + o]);
     __syncthreads();
   }
   if (threadIdx.x == 0) p.out[0] = best[0];   // .max() :1001

@@ -254,6 +254,16 @@ __host__ __device__ __forceinline__ bool recip_div_ok(float d) {
 }
 
 // ---- per-element arithmetic -----------------------------------------------------------------
+// torch.clamp(x0, -s, s) (:424) for s >= 0, NaN-propagating like ATen's clamp: fminf/fmaxf would turn a NaN x0
+// into -s; with comparisons a NaN x0 (every comparison false) passes through, and a NaN s reaches the result
+// through the division that follows.
+__device__ __forceinline__ float clamp_sym(float x0, float s) {
+  return x0 > s ? s : (x0 < -s ? -s : x0);
+}
+// torch.maximum / Tensor.max(): NaN wins
+__device__ __forceinline__ float max_nan(float a, float b) {
+  return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+}
 // model_wrapper.noise_pred_fn :288-298
 __device__ __forceinline__ float convert_param(int param, float out, float xe, float alpha,
                                                float sigma) {
@@ -284,7 +294,7 @@ __device__ __forceinline__ float model_value(const KParams& p, float xe, float e
   }
   if (p.predict_x0) {
     float x0 = (xe - p.sigma_e * eps) / p.alpha_e;  // data_prediction_fn :439
-    if (clamp) x0 = fminf(fmaxf(x0, -thr), thr) / thr;  // dynamic_thresholding_fn :424
+    if (clamp) x0 = clamp_sym(x0, thr) / thr;  // dynamic_thresholding_fn :424
     return x0;
   }
   return eps;
@@ -317,11 +327,11 @@ __device__ __forceinline__ void model_values8(const KParams& p, const float (&xe
       if (recip_div_ok(s)) {
         const float rs = __frcp_rn(s);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x0[i] = fminf(fmaxf(x0[i], -s), s);
+        for (int i = 0; i < 8; ++i) x0[i] = clamp_sym(x0[i], s);
         div_const8(x0, s, rs);  // :424
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x0[i] = fminf(fmaxf(x0[i], -s), s) / s;
+        for (int i = 0; i < 8; ++i) x0[i] = clamp_sym(x0[i], s) / s;
       }
     }
 #pragma unroll

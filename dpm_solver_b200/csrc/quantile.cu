@@ -53,7 +53,8 @@ struct QParams {
   uint32_t num_space; // pipeline: bracket keys are |numerator| patterns (plain eps -> x0 map, alpha > 0)
 };
 // header words per sample
-enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_WORDS = 8 };
+enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_NAN = 7, H_WORDS = 8 };
+constexpr uint32_t kInfKey = 0x7f800000u;   // |x0| bit patterns above this are NaN: torch.quantile then returns NaN
 
 struct Sel {
   uint32_t bin, cnt;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(kPThreads) k_q_pivots(const __grid_constant__ 
     h[H_HI] = s_piv[1];
     h[H_LT] = 0u;
     h[H_IN] = 0u;
+    h[H_NAN] = 0u;
     // The same two thresholds in "numerator space". x0 = RN(num / alpha) with num = xe - sigma*eps
     // is a monotone non-decreasing function of |num|, so
     //   key(x0) <  lo  <=>  |num| <  A_lo,   A_lo = min{a : RN(a/alpha) >= float(lo)}
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
   if (tid == 0) { s_n = 0; s_lt = 0; }
   __syncthreads();
 
-  uint32_t c_lt = 0;
+  uint32_t c_lt = 0, kmax = 0;   // kmax: largest |.| bit pattern seen (NaN detection, one integer max per element)
   // numerator space: 8 elements, ~8 instructions each and NO division at all: |num| -> |num / alpha| is
   // monotone for alpha > 0, so the bracket keys are collected as |num| bit patterns and k_q_finish
   // selects among them by rank and divides only the two order statistics it returns. One shared-memory
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
     for (int i = 0; i < 8; ++i) {
       const float eps = (NE == 2) ? fu[i] + p.guidance * (fc[i] - fu[i]) : fc[i];   // :330
       a8[i] = fabsf(fx[i] - p.sigma_e * eps);                                        // |numerator| of :439
+      kmax = max(kmax, __float_as_uint(a8[i]));
       const bool ge = a8[i] >= A_lo;
       n_ge += ge ? 1u : 0u;
       mask |= (ge && a8[i] <= A_hi) ? (1u << i) : 0u;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool ge = k8[i] >= lo_k;
+      kmax = max(kmax, k8[i]);
       c_lt += ge ? 0u : 1u;
       mask |= (ge && k8[i] <= hi_k) ? (1u << i) : 0u;
     }
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
     }
   };
   auto visit = [&](uint32_t k) {
+    kmax = max(kmax, k);
     c_lt += k < lo_k ? 1u : 0u;
     if (k >= lo_k && k <= hi_k) {
       const uint32_t pos = atomicAdd(&s_n, 1u);
@@ -337,6 +342,8 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c_lt += __shfl_xor_sync(0xffffffffu, c_lt, o);
   if ((tid & 31) == 0 && c_lt) atomicAdd(&s_lt, c_lt);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if ((tid & 31) == 0 && kmax > kInfKey) atomicOr(&hdr[H_NAN], 1u);
   __syncthreads();
   const uint32_t n_local = s_n;
   if (tid == 0) {
@@ -433,7 +440,8 @@ __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ 
       k_lo = __float_as_uint(__fdiv_rn(__uint_as_float(key_lo), p.alpha_e));
       k_hi = __float_as_uint(__fdiv_rn(__uint_as_float(key_hi), p.alpha_e));
     }
-    qp.s_out[sample] = finish_value(k_lo, k_hi, qp);
+    // a NaN anywhere in the sample makes torch.quantile (and the maximum that follows, :422-423) return NaN
+    qp.s_out[sample] = hdr[H_NAN] ? __uint_as_float(0x7fc00000u) : finish_value(k_lo, k_hi, qp);
   }
 }
 
@@ -448,6 +456,7 @@ __global__ void __launch_bounds__(kQThreads)
   uint32_t* keys = ctrl + 64;                                      // [cap]
   uint32_t* warp_sums = ctrl;                                      // 16 used
   uint32_t* min_slot = ctrl + 32;
+  uint32_t* max_slot = ctrl + 33;                                  // largest key of the sample (NaN detection)
   Sel* sel = reinterpret_cast<Sel*>(ctrl + 40);
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -465,7 +474,8 @@ __global__ void __launch_bounds__(kQThreads)
 
   for (int i = tid; i < kBins; i += kQThreads) hist[i] = 0;
   for (int i = tid; i < 3 * kBins; i += kQThreads) total[i] = 0;
-  if (tid == 0) *min_slot = 0xffffffffu;
+  if (tid == 0) { *min_slot = 0xffffffffu; *max_slot = 0u; }
+  uint32_t kmax = 0;
   __syncthreads();
 
   const TS* __restrict__ gxe = static_cast<const TS*>(p.xe);
@@ -506,7 +516,7 @@ __global__ void __launch_bounds__(kQThreads)
           uint32_t k8[8];
           keys_of_packet<NE>(p, rx[u], rc[u], ru[u], k8);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) atomicAdd(&hist[k8[i] >> 21], 1u);
+          for (int i = 0; i < 8; ++i) { atomicAdd(&hist[k8[i] >> 21], 1u); kmax = max(kmax, k8[i]); }
           if (qp.cap) {
             uint4* dst = reinterpret_cast<uint4*>(keys + (size_t)pk * kPacket);
             dst[0] = make_uint4(k8[0], k8[1], k8[2], k8[3]);
@@ -518,6 +528,7 @@ __global__ void __launch_bounds__(kQThreads)
   } else {
     for (uint32_t i = tid; i < cnt; i += kQThreads) {
       uint32_t k = key_scalar(i);
+      kmax = max(kmax, k);
       atomicAdd(&hist[k >> 21], 1u);
       if (qp.cap) keys[i] = k;
     }
@@ -526,10 +537,13 @@ __global__ void __launch_bounds__(kQThreads)
 
   uint32_t* total0 = csize > 1 ? cluster.map_shared_rank(total, 0) : total;
   uint32_t* min0 = csize > 1 ? cluster.map_shared_rank(min_slot, 0) : min_slot;
+  uint32_t* max0 = csize > 1 ? cluster.map_shared_rank(max_slot, 0) : max_slot;
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
 
   auto merge = [&](int pass, int nb) {
     __syncthreads();
     if (pass == 0 && csize > 1) cluster.sync();  // every CTA has zeroed its arrays
+    if (pass == 0 && (tid & 31) == 0 && kmax > kInfKey) atomicMax(max0, kmax);
     for (int i = tid; i < nb; i += kQThreads) {
       uint32_t v = hist[i];
       if (v) atomicAdd(&total0[pass * kBins + i], v);
@@ -583,6 +597,7 @@ __global__ void __launch_bounds__(kQThreads)
     // at::native::lerp, CPU vectorised path: fmadd(coeff, end - start, base)
     float s = qp.w < 0.5f ? fmaf(qp.w, d, a) : fmaf(qp.w - 1.f, d, b);
     s = fmaxf(s, qp.max_val);  // torch.maximum(s, max_val) :423
+    if (*max0 > kInfKey) s = __uint_as_float(0x7fc00000u);   // NaN in the sample: torch.quantile returns NaN
     qp.s_out[sample] = s;
   }
   if (csize > 1) cluster.sync();  // keep CTA 0's shared memory alive until every peer has read it
@@ -642,6 +657,8 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
   else if (md == DPM_F16 && sd == DPM_F16) DPM_PICK(__half, __half)
   else if (md == DPM_BF16 && sd == DPM_F32) DPM_PICK(__nv_bfloat16, float)
   else if (md == DPM_F16 && sd == DPM_F32) DPM_PICK(__half, float)
+  else if (md == DPM_F32 && sd == DPM_BF16) DPM_PICK(float, __nv_bfloat16)   // fp32 network output, 16-bit state
+  else if (md == DPM_F32 && sd == DPM_F16) DPM_PICK(float, __half)
   else { set_error("dynamic threshold: unsupported dtype mix (model %d, state %d)", md, sd); return DPM_ERR_UNSUPPORTED; }
 #undef DPM_PICK
 

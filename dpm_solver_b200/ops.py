@@ -191,8 +191,8 @@ class CudaBackend:
             d.out = out.data_ptr()
             if a.out2 is not None:
                 self._check(a.out2, "out2", ref.device, ref.numel(), sdt)
-                if not a.out2.is_contiguous():
-                    raise ValueError("dpm_solver_b200: out2 must be contiguous")
+                if self._layout(a.out2) != layout:      # dense, laid out like `out` (a channels_last half of the
+                    raise ValueError("dpm_solver_b200: out2 must be dense and laid out like out")   # doubled CFG batch is)
                 d.out2 = a.out2.data_ptr()
         self._launch(ref.device, self._lib.dpm_step, C.byref(d))
         return m_out, out

@@ -396,6 +396,20 @@ class DPM_Solver:
             cache[k] = hit
         return hit
 
+    def _denoise_tables(self, t_0, batch, device):
+        """(device label (1,), model-input time row or None, (alpha, sigma)) of the denoise-to-zero tail."""
+        cache = self.__dict__.setdefault("_table_cache", {})
+        k = (self._schedule_key(), "d2z", float(t_0), batch, str(device), id(self._wrapped))
+        hit = cache.get(k)
+        if hit is None:
+            th = torch.ones((1,)) * t_0                                   # fp32, as `torch.ones((1,)).to(device) * t_0`
+            tin = self._input_times(th, batch, device)
+            hit = (self._upload(th, device), None if tin is None else tin[0], self._alpha_sigma(th))
+            if len(cache) >= self._CACHE_MAX:
+                cache.pop(next(iter(cache)))
+            cache[k] = hit
+        return hit
+
     @staticmethod
     def _upload(t_host: torch.Tensor, device):
         """Host vector -> device without draining the stream (pinned staging, async copy)."""
@@ -754,6 +768,9 @@ class DPM_Solver:
                 E = E.reshape(1).float()
                 dist.all_reduce(E, op=dist.ReduceOp.MAX)
             E = E.cpu()
+            if bool(torch.isnan(E).any()):
+                # the reference would reject the step, set h = NaN and spin forever (s never advances, :1002-1008)
+                raise FloatingPointError("dpm_solver_adaptive: the error estimate is NaN (the network output diverged)")
             if torch.all(E <= 1.):
                 x = x_higher
                 s = t
@@ -771,7 +788,8 @@ class DPM_Solver:
         alpha_t, sigma_t = self.noise_schedule.marginal_alpha(th), self.noise_schedule.marginal_std(th)
         if noise is None:
             noise = torch.randn((th.shape[0], *x.shape), device=x.device)
-        xs = self._state_like(x, x.dtype if x.dtype in ops.SUPPORTED_DTYPES else torch.float32)
+        # result dtype: the reference's fp32 (t_size,1,..) coefficient tensors promote a 16-bit x to fp32 (:1026)
+        xs = self._state_like(x, self._sdtype(x))
         noise = noise.reshape((th.shape[0], *x.shape))
         outs = [ops.lincomb(xs, [self._state_like(noise[i], xs.dtype)], float(alpha_t[i]), [float(sigma_t[i])])
                 for i in range(th.shape[0])]
@@ -921,13 +939,16 @@ class DPM_Solver:
                         r1 = None if o <= 1 else (lambda_inner[1] - lambda_inner[0]) / h
                         r2 = None if o <= 2 else (lambda_inner[2] - lambda_inner[0]) / h
                         plans.append(P.singlestep_plan(ns, self.algorithm_type, solver_type, o, s_, t_, r1, r2))
+                    if not plans:
+                        # steps < order with 'singlestep_fixed': K = 0, the reference runs no outer step (:1216-1220)
+                        return timesteps_outer.reshape(-1), plans, []
                     all_times = torch.cat([tt.reshape(-1) for sp in plans for tt in sp.times])
                     marg = P.Marginals(ns, all_times)
                     return (torch.cat([all_times, timesteps_outer.reshape(-1)]), plans,
                             list(zip(marg.alpha.tolist(), marg.sigma.tolist())))
 
                 packed, plans, alsig = self._host_plan(key, build)
-                if self.plan_broadcast:
+                if self.plan_broadcast and plans:
                     flat = self._sync_plan([co for sp in plans for co in sp.stages], key)
                     plans = [P.SinglestepPlan(sp.order, sp.times, []) for sp in plans]
                     k = 0
@@ -936,8 +957,8 @@ class DPM_Solver:
                         sp.stages = flat[k:k + n_st]
                         k += n_st
                 n_eval = len(alsig)
-                packed_dev, tin = self._device_tables(key, packed, x.shape[0], device, n_eval)
-                all_dev, outer_dev = packed_dev[:n_eval], packed_dev[n_eval:]
+                packed_dev, tin = self._device_tables(key, packed, x.shape[0], device, n_eval) if plans else (None, None)
+                all_dev, outer_dev = (packed_dev[:n_eval], packed_dev[n_eval:]) if plans else (None, None)
                 k = 0
                 step = 0
                 for step, sp in enumerate(plans):
@@ -954,8 +975,11 @@ class DPM_Solver:
             else:
                 raise ValueError("Got wrong method {}".format(method))
             if denoise_to_zero:
-                t = torch.ones((1,)).to(device) * t_0
-                x = self.denoise_to_zero_fn(x, t)
+                # :1236-1238. The label, its model-input time and (alpha, sigma) at t_0 are cached with the tables:
+                # no host<->device traffic in the steady state, so the tail is CUDA-graph capturable too
+                t, tin0, als0 = self._denoise_tables(t_0, x.shape[0], device)
+                xs = self._state(x)
+                x = self._post_model(self._evaluate(xs, t, tin0), xs, t, als0, x0=True)[0]
                 if self.correcting_xt_fn is not None:
                     x = self.correcting_xt_fn(x, t, step + 1)
                 if return_intermediate:

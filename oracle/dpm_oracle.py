@@ -317,6 +317,9 @@ def quantile_abs(x0, q):
     w = np.float32(pos - np.float32(lo))
     out = np.empty((a.shape[0],), dtype=np.float32)
     for b in range(a.shape[0]):
+        if np.isnan(srt[b, -1]):          # numpy sorts NaN last; torch.quantile returns NaN when the row holds one
+            out[b] = np.float32(np.nan)
+            continue
         vl, vh = srt[b, lo], srt[b, min(hi, n - 1)]
         d = np.float32(vh - vl)
         out[b] = _fma32(w, d, vl) if w < np.float32(0.5) else _fma32(np.float32(w - np.float32(1)), d, vh)

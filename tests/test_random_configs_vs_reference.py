@@ -323,3 +323,18 @@ def test_hooks_match_reference(oracle_backend, method, order, steps, cfg):
     np.testing.assert_array_equal(outs[1][0].numpy(), outs[0][0].numpy())
     for a, b in zip(outs[1][1], outs[0][1]):
         np.testing.assert_array_equal(a.numpy(), b.numpy())
+
+
+@pytest.mark.parametrize("steps,order", [(2, 3), (1, 2), (1, 3)])
+def test_singlestep_fixed_with_fewer_steps_than_order(oracle_backend, steps, order):
+    """K = steps // order = 0: the reference runs no outer step and returns x (plus the optional denoise tail)."""
+    import dpm_solver_b200 as new
+    ref = reference_module()
+    for d2z in (False, True):
+        c = dict(schedule="sd", algo="dpmsolver++", method="singlestep_fixed", order=order, steps=steps, skip_type="time_uniform",
+                 solver_type="dpmsolver", model_type="noise", cfg=None, lower_order_final=True, denoise_to_zero=d2z, t_end=None,
+                 seed=5, thresholding=False)
+        yr, ir, cr = run(ref.NoiseScheduleVP, ref.model_wrapper, ref.DPM_Solver, c)
+        yn, in_, cn = run(new.NoiseScheduleVP, new.model_wrapper, new.DPM_Solver, c)
+        assert cn == cr and len(in_) == len(ir)
+        np.testing.assert_array_equal(yn.numpy(), yr.numpy())
