@@ -202,13 +202,19 @@ __device__ __forceinline__ float round_any(int dt, float v) {
 // ---- exact division by a launch constant -------------------------------------------------------
 // x / d for a divisor that is uniform over the launch, without the per-element IEEE division
 // subroutine (MUFU.RCP + 4 FFMA + FCHK + slow-path call). With r = RN(1/d) prepared once:
-//   q0 = RN(x*r); e = x - q0*d (exact, one FMA); q1 = RN(q0 + e*r); repeat once.
-// q0 is within 2 ulp of x/d, each refinement with the exact residual contracts the error below
-// half an ulp, and a second pass leaves a correctly rounded quotient unchanged (Markstein's
-// division theorem; it needs d's significand not to be all ones -- checked on the host -- and no
-// underflow/overflow in the residual, guarded below by routing tiny/huge/non-finite x to the IEEE
-// division). tests/test_gpu_kernels.py::test_constant_division_is_ieee compares it bit for bit
-// with true division over ~10^9 (x, d) pairs. Explicit fmaf() stays fused under -fmad=false.
+//   q0 = RN(x*r); e = x - q0*d (one FMA); q1 = RN(q0 + e*r); repeat once.
+// q0 can be up to ~1.4 ulp from x/d (half an ulp of r's error scaled to the quotient plus the product's
+// rounding), so its residual need not be exact; q1 is faithful (within an ulp), the residual of a
+// faithful quotient IS exact in one FMA, and Markstein's division theorem then makes the second
+// refinement the correctly rounded quotient -- provided d's significand is not all ones (checked on
+// the host, recip_div_ok) and nothing under/overflows in the residual, guarded below by routing
+// tiny/huge/non-finite/zero x to the IEEE division. (One refinement alone matched IEEE on 4e8 random
+// pairs but is not provable: its error bound, 1.7e-7 ulp, exceeds the closest a quotient can come to
+// a rounding midpoint, 1.5e-8 ulp.) tests/test_gpu_kernels.py::test_constant_division_is_ieee compares
+// it bit for bit with true division over ~10^9 (x, d) pairs; tests/test_math_properties.py repeats the
+// argument in exact rational arithmetic. Explicit fmaf() stays fused under -fmad=false.
+static __device__ __noinline__ float div_ieee_cold(float x, float d) { return x / d; }
+
 __device__ __forceinline__ float div_const(float x, float d, float r) {
   float q = x * r;
   float e = fmaf(-q, d, x);
@@ -216,13 +222,15 @@ __device__ __forceinline__ float div_const(float x, float d, float r) {
   e = fmaf(-q, d, x);
   q = fmaf(e, r, q);
   const float ax = fabsf(x);
-  if (!(ax > 1e-25f && ax < 1e30f)) q = x / d;  // zero, tiny, huge, inf, nan: IEEE path
+  if (!(ax > 1e-25f && ax < 1e30f)) q = div_ieee_cold(x, d);  // zero, tiny, huge, inf, nan: IEEE path
   return q;
 }
-// packet form: one range guard (and one cold IEEE block) per 8 elements instead of per element
+// packet form: the range guard is one min and one max over the 8 magnitudes (a NaN that the min/max
+// skip still comes out of the refinement as NaN) and one never-inlined IEEE call site per element,
+// off the hot path
 __device__ __forceinline__ void div_const8(float (&x)[8], float d, float r) {
   float q[8];
-  bool bad = false;
+  float mn = fabsf(x[0]), mx = mn;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float t = x[i] * r;
@@ -230,12 +238,14 @@ __device__ __forceinline__ void div_const8(float (&x)[8], float d, float r) {
     t = fmaf(e, r, t);
     e = fmaf(-t, d, x[i]);
     q[i] = fmaf(e, r, t);
-    const float ax = fabsf(x[i]);
-    bad |= !(ax > 1e-25f && ax < 1e30f);
+    if (i > 0) {
+      mn = fminf(mn, fabsf(x[i]));
+      mx = fmaxf(mx, fabsf(x[i]));
+    }
   }
-  if (bad) {
+  if (!(mn > 1e-25f && mx < 1e30f)) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = x[i] / d;
+    for (int i = 0; i < 8; ++i) q[i] = div_ieee_cold(x[i], d);   // fully unrolled: a dynamic index would put q[] in local memory
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = q[i];
@@ -395,6 +405,72 @@ __device__ __forceinline__ float update_value(const KParams& p, float x, float T
     return ((p.a * x + p.c0 * m2) + p.c1 * D1) + p.c2 * D2;  // :745-750 / :784-789
   }
   return 0.f;
+}
+
+// ---- the fast path: noise-parameterised networks (the common case), exact constant division ------
+// Launch-uniform switches are taken once per PACKET (uniform branches), every loop below is
+// straight-line code over 8 elements. Callers guarantee: p.param == NOISE; p.fast_div when a division
+// is needed; a clamp threshold `s` that is uniform over the packet.
+template <int NE>
+__device__ __forceinline__ void fast_model8(const KParams& p, const float (&xe)[8], const float (&ec)[8],
+                                            const float (&eu)[8], bool clamp, float s, float (&T)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) T[i] = (NE == 2) ? eu[i] + p.guidance * (ec[i] - eu[i]) : ec[i];  // :330
+  if (!p.predict_x0) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) T[i] = xe[i] - p.sigma_e * T[i];
+  div_const8(T, p.alpha_e, p.r_alpha);  // :439
+  if (clamp) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[i] = clamp_sym(T[i], s);
+    if (recip_div_ok(s)) {
+      div_const8(T, s, __frcp_rn(s));  // :424
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) T[i] = div_ieee_cold(T[i], s);
+    }
+  }
+}
+
+template <int FORM>
+__device__ __forceinline__ void fast_update8(const KParams& p, const float (&x)[8], const float (&T)[8],
+                                             const float (&m1)[8], const float (&m2)[8], float (&o)[8]) {
+  if (FORM == DPM_FORM_DIFF2) {
+    // the coefficient sits on model_s for the singlestep difference steps: one uniform branch per packet
+    if (p.c0_on_old) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (p.a * x[i] + p.c0 * m1[i]) + p.c1 * (p.w0 * (T[i] - m1[i]));  // :636-669, :728-739
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (p.a * x[i] + p.c0 * T[i]) + p.c1 * (p.w0 * (T[i] - m1[i]));   // :823-851
+    }
+  } else if (FORM == DPM_FORM_SS3T) {
+    float n1[8], n2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float D10 = p.w0 * (m1[i] - m2[i]);  // :741
+      const float D11 = p.w1 * (T[i] - m2[i]);   // :742
+      n1[i] = p.w2 * D10 - p.w3 * D11;
+      n2[i] = 2.f * (D11 - D10);
+    }
+    div_const8(n1, p.w4, p.r_w4);  // :743
+    div_const8(n2, p.w4, p.r_w4);  // :744
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = ((p.a * x[i] + p.c0 * m2[i]) + p.c1 * n1[i]) + p.c2 * n2[i];  // :745-750 / :784-789
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = update_value<FORM>(p, x[i], T[i], m1[i], m2[i]);
+  }
+}
+
+// launch-time test: can this request run on the <FAST = true> instantiations?
+__host__ __forceinline__ bool fast_path_ok(const KParams& p) {
+  if (p.form == DPM_FORM_SS3T && !p.fast_div) return false;
+  if (p.n_model == 0) return true;
+  if (p.param != DPM_PARAM_NOISE) return false;
+  if (p.predict_x0 && !p.fast_div) return false;
+  if (p.thr != nullptr && p.pk_per_sample == 0) return false;
+  return true;
 }
 
 // compile-time stream requirements of a form

@@ -14,7 +14,9 @@ namespace dpm {
 constexpr int kUnroll = DPM_UNROLL;
 constexpr int kMaxThreads = 512;
 
-template <typename TE, typename TS, int NE, int FORM>
+// FAST: the straight-line packet code of common.cuh (fast_model8 / fast_update8; launch-time test
+// fast_path_ok). FAST = false keeps every parameterisation, per-element thresholds and IEEE divisions.
+template <typename TE, typename TS, int NE, int FORM, bool FAST>
 __global__ void __launch_bounds__(kMaxThreads)
     k_step_direct(const __grid_constant__ KParams p) {
   using Needs = FormNeeds<FORM>;
@@ -66,7 +68,21 @@ __global__ void __launch_bounds__(kMaxThreads)
         if (Needs::kX) unpack(rx[u], fx);
         if (Needs::kM1) unpack(rm1[u], fm1);
         if (Needs::kM2) unpack(rm2[u], fm2);
-        if (NE > 0) {
+        if (NE > 0 && FAST) {
+          float fec[8], feu[8];
+          unpack(rec[u], fec);
+          if (NE == 2) unpack(reu[u], feu);
+          const float s_thr = clamp ? __ldg(p.thr + (uint32_t)pk / p.pk_per_sample) : 1.f;   // packet index < 2^32 (npk)
+          if (sep_xe) {
+            unpack(rxe[u], fxe);
+            fast_model8<NE>(p, fxe, fec, feu, clamp, s_thr, fT);
+          } else {
+            fast_model8<NE>(p, fx, fec, feu, clamp, s_thr, fT);   // fx is only read when predict_x0 (then it is loaded)
+          }
+          Raw<TS> rmo;
+          round_pack(rmo, fT);
+          if (gmo != nullptr) stg_pk(gmo + e, rmo);
+        } else if (NE > 0) {
           float fec[8], feu[8];
           unpack(rec[u], fec);
           if (NE == 2) unpack(reu[u], feu);
@@ -94,11 +110,9 @@ __global__ void __launch_bounds__(kMaxThreads)
 #pragma unroll
             for (int i = 0; i < 8; ++i) thr8[i] = 1.f;
           }
-          if (NE != 2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) feu[i] = 0.f;
-          }
-          model_values8<NE>(p, fxe, fec, feu, thr8, clamp, thr_uniform, fT);
+          for (int i = 0; i < 8; ++i)
+            fT[i] = model_value<NE>(p, fxe[i], fec[i], NE == 2 ? feu[i] : 0.f, thr8[i], clamp);
           Raw<TS> rmo;
           round_pack(rmo, fT);
           if (gmo != nullptr) stg_pk(gmo + e, rmo);
@@ -106,10 +120,14 @@ __global__ void __launch_bounds__(kMaxThreads)
           unpack(rm0[u], fT);
         }
         if (FORM != DPM_FORM_NONE) {
+          if (FAST) {
+            fast_update8<FORM>(p, fx, fT, fm1, fm2, fo);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f,
-                                       Needs::kM2 ? fm2[i] : 0.f);
+            for (int i = 0; i < 8; ++i)
+              fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f,
+                                         Needs::kM2 ? fm2[i] : 0.f);
+          }
           Raw<TS> ro;
           pack(ro, fo);
           stg_pk(go + e, ro);
@@ -167,46 +185,53 @@ __global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KPa
 // ---- dispatch ---------------------------------------------------------------------------------
 typedef void (*StepKernel)(const KParams);
 
-template <typename TE, typename TS, int NE>
+// NE == 0 has no model conversion: only SS3T (division by w4) has a generic twin there.
+template <typename TE, typename TS, int NE, bool FAST>
 static StepKernel pick_form(int form) {
+  constexpr bool kTwin = NE > 0 || !FAST;   // is <FAST = false> a distinct kernel for this (NE, form)?
   switch (form) {
-    case DPM_FORM_NONE: return NE > 0 ? k_step_direct<TE, TS, NE, DPM_FORM_NONE> : nullptr;
-    case DPM_FORM_LIN1: return k_step_direct<TE, TS, NE, DPM_FORM_LIN1>;
-    case DPM_FORM_LIN2: return k_step_direct<TE, TS, NE, DPM_FORM_LIN2>;
-    case DPM_FORM_LIN3: return k_step_direct<TE, TS, NE, DPM_FORM_LIN3>;
-    case DPM_FORM_DIFF2: return k_step_direct<TE, TS, NE, DPM_FORM_DIFF2>;
-    case DPM_FORM_MS3: return k_step_direct<TE, TS, NE, DPM_FORM_MS3>;
-    case DPM_FORM_SS3T: return k_step_direct<TE, TS, NE, DPM_FORM_SS3T>;
+    case DPM_FORM_NONE: return NE > 0 ? k_step_direct<TE, TS, NE, DPM_FORM_NONE, FAST> : nullptr;
+    case DPM_FORM_LIN1: return k_step_direct<TE, TS, NE, DPM_FORM_LIN1, FAST || NE == 0>;
+    case DPM_FORM_LIN2: return k_step_direct<TE, TS, NE, DPM_FORM_LIN2, FAST || NE == 0>;
+    case DPM_FORM_LIN3: return k_step_direct<TE, TS, NE, DPM_FORM_LIN3, FAST || NE == 0>;
+    case DPM_FORM_DIFF2: return k_step_direct<TE, TS, NE, DPM_FORM_DIFF2, FAST || NE == 0>;
+    case DPM_FORM_MS3: return k_step_direct<TE, TS, NE, DPM_FORM_MS3, FAST || NE == 0>;
+    case DPM_FORM_SS3T: return k_step_direct<TE, TS, NE, DPM_FORM_SS3T, FAST>;
   }
+  (void)kTwin;
   return nullptr;
+}
+template <typename TE, typename TS, int NE>
+static StepKernel pick_fast(int form, bool fast) {
+  return fast ? pick_form<TE, TS, NE, true>(form) : pick_form<TE, TS, NE, false>(form);
 }
 template <typename TE, typename TS>
-static StepKernel pick_ne(int ne, int form) {
+static StepKernel pick_ne(int ne, int form, bool fast) {
   switch (ne) {
-    case 1: return pick_form<TE, TS, 1>(form);
-    case 2: return pick_form<TE, TS, 2>(form);
+    case 1: return pick_fast<TE, TS, 1>(form, fast);
+    case 2: return pick_fast<TE, TS, 2>(form, fast);
   }
   return nullptr;
 }
-static StepKernel pick_direct(int md, int sd, int ne, int form) {
+static StepKernel pick_direct(int md, int sd, int ne, int form, bool fast) {
   if (ne == 0) {
     switch (sd) {
-      case DPM_F32: return pick_form<float, float, 0>(form);
-      case DPM_BF16: return pick_form<__nv_bfloat16, __nv_bfloat16, 0>(form);
-      case DPM_F16: return pick_form<__half, __half, 0>(form);
+      case DPM_F32: return pick_fast<float, float, 0>(form, fast);
+      case DPM_BF16: return pick_fast<__nv_bfloat16, __nv_bfloat16, 0>(form, fast);
+      case DPM_F16: return pick_fast<__half, __half, 0>(form, fast);
     }
     return nullptr;
   }
-  if (md == DPM_F32 && sd == DPM_F32) return pick_ne<float, float>(ne, form);
-  if (md == DPM_BF16 && sd == DPM_BF16) return pick_ne<__nv_bfloat16, __nv_bfloat16>(ne, form);
-  if (md == DPM_F16 && sd == DPM_F16) return pick_ne<__half, __half>(ne, form);
-  if (md == DPM_BF16 && sd == DPM_F32) return pick_ne<__nv_bfloat16, float>(ne, form);
-  if (md == DPM_F16 && sd == DPM_F32) return pick_ne<__half, float>(ne, form);
+  if (md == DPM_F32 && sd == DPM_F32) return pick_ne<float, float>(ne, form, fast);
+  if (md == DPM_BF16 && sd == DPM_BF16) return pick_ne<__nv_bfloat16, __nv_bfloat16>(ne, form, fast);
+  if (md == DPM_F16 && sd == DPM_F16) return pick_ne<__half, __half>(ne, form, fast);
+  if (md == DPM_BF16 && sd == DPM_F32) return pick_ne<__nv_bfloat16, float>(ne, form, fast);
+  if (md == DPM_F16 && sd == DPM_F32) return pick_ne<__half, float>(ne, form, fast);
   return nullptr;  // other mixes run on the generic kernel
 }
 
 int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream) {
-  StepKernel k = pick_direct(p.model_dtype, p.state_dtype, p.n_model, p.form);
+  StepKernel k = pick_direct(p.model_dtype, p.state_dtype, p.n_model, p.form, fast_path_ok(p));
   if (k == nullptr) return 1;  // not served here
   const int threads = t.threads > 0 ? t.threads : 256;
   const uint32_t tile_pk = (uint32_t)threads * kUnroll;

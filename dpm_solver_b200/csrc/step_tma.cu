@@ -1,4 +1,5 @@
-// step_tma.cu -- variant 1: TMA bulk staging through a shared-memory ring.
+// step_tma.cu -- variant 1: TMA bulk staging through a shared-memory ring (fast path only: noise-parameterised
+// networks, exact constant division -- common.cuh fast_model8 / fast_update8).
 //
 // Persistent CTAs. One elected thread moves whole tiles with 1-D bulk async copies
 // (cp.async.bulk, SASS UBLKCP): global -> shared completes on an mbarrier (complete_tx),
@@ -161,27 +162,15 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
           float fec[8], feu[8];
           { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.ec) + le); unpack(r, fec); }
           if (NE == 2) { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.eu) + le); unpack(r, feu); }
-          const uint64_t pk = e0 / kPacket + lp;
-          float thr8[8], fxe[8];
-          const bool thr_uniform = p.pk_per_sample != 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            thr8[i] = 1.f;
-            fxe[i] = has_x ? fx[i] : 0.f;
-            if (NE != 2) feu[i] = 0.f;
+          // per-sample threshold: uniform over the packet (fast path: per_sample % 8 == 0)
+          const float s_thr = clamp ? __ldg(p.thr + ((uint32_t)(e0 / kPacket) + lp) / p.pk_per_sample) : 1.f;   // packet index < 2^32 (npk)
+          if (sep_xe) {
+            float fxe[8];
+            { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.xe) + le); unpack(r, fxe); }
+            fast_model8<NE>(p, fxe, fec, feu, clamp, s_thr, fT);
+          } else {
+            fast_model8<NE>(p, fx, fec, feu, clamp, s_thr, fT);   // fx is only read when predict_x0 (then has_x)
           }
-          if (sep_xe) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.xe) + le); unpack(r, fxe); }
-          if (clamp) {
-            if (thr_uniform) {
-              const float tpk = __ldg(p.thr + (uint32_t)(pk / p.pk_per_sample));
-#pragma unroll
-              for (int i = 0; i < 8; ++i) thr8[i] = tpk;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) thr8[i] = __ldg(p.thr + (e0 + le + i) / p.per_sample);
-            }
-          }
-          model_values8<NE>(p, fxe, fec, feu, thr8, clamp, thr_uniform, fT);
           Raw<TS> rmo;
           round_pack(rmo, fT);
           if (has_mo) sts_pk(reinterpret_cast<TS*>(st + L.mo) + le, rmo);
@@ -189,9 +178,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
           Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m0) + le); unpack(r, fT);
         }
         if (FORM != DPM_FORM_NONE) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f, Needs::kM2 ? fm2[i] : 0.f);
+          fast_update8<FORM>(p, fx, fT, fm1, fm2, fo);
           Raw<TS> r; pack(r, fo); sts_pk(reinterpret_cast<TS*>(st + L.o) + le, r);
         }
       }
@@ -253,6 +240,7 @@ static TmaKernel pick_tma(int md, int sd, int ne, int form) {
 }
 
 int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
+  if (!fast_path_ok(p)) return 1;   // other parameterisations / non-refinable divisors: the direct variant's generic kernels
   const bool need_x = p.form != DPM_FORM_NONE;
   TmaKernel k = pick_tma(p.model_dtype, p.state_dtype, p.n_model, p.form);
   if (k == nullptr) return 1;

@@ -43,15 +43,23 @@ def _launches():
 
 
 @pytest.mark.parametrize("order,steps,method", [(2, 20, "multistep"), (3, 12, "multistep"), (2, 9, "singlestep")])
-def test_stable_diffusion_adapter_runs_unchanged(product_device, order, steps, method):
+@pytest.mark.parametrize("tables", ["host", "device"])
+def test_stable_diffusion_adapter_runs_unchanged(product_device, order, steps, method, tables):
+    """tables="device": the adapter's own behaviour on a GPU -- it moves alphas_cumprod to the device
+    (sampler.py:23-27), so NoiseScheduleVP takes its log() THERE and the schedule table differs from a CPU-built
+    one in the last ulp of a few entries: the product is then within the north-star tolerance of the CPU reference.
+    tables="host": the same adapter with the table kept on the host -> bit-identical."""
     import dpm_solver_b200
+    if product_device == "cpu" and tables == "device":
+        pytest.skip("same as host on the CPU executor")
     B, shape = 2, (4, 16, 16)
     x_T = torch.randn(B, *shape, generator=torch.Generator().manual_seed(3))
     outs = []
     before = _launches()
     for tag, solver, dev in (("ref", A.reference_solver("sd"), "cpu"), ("b200", dpm_solver_b200, product_device)):
-        mod = A.load_sd_adapter(solver, tag + product_device.replace(":", ""), dev)
-        model = A.StubLatentDiffusion(dev)
+        tdev = dev if tables == "device" else "cpu"
+        mod = A.load_sd_adapter(solver, tag + product_device.replace(":", "") + tables, tdev)
+        model = A.StubLatentDiffusion(tdev)
         sampler = mod.DPMSolverSampler(model)
         assert sampler.noise_schedule.total_N == 1000
         cond, uncond = torch.ones(B, 1, device=dev), torch.zeros(B, 1, device=dev)
@@ -67,12 +75,16 @@ def test_stable_diffusion_adapter_runs_unchanged(product_device, order, steps, m
         assert _launches() > before, "the CUDA library did not run"
     assert [c[1] for c in cr] == [c[1] for c in cn]     # same network calls: doubled batch ...
     np.testing.assert_allclose([c[0] for c in cn], [c[0] for c in cr], rtol=1e-6)   # ... same time labels
-    np.testing.assert_array_equal(xn.numpy(), xr.numpy())
     assert len(ir) == len(in_)
-    for a, b in zip(ir, in_):
-        np.testing.assert_array_equal(b.numpy(), a.numpy())
-    np.testing.assert_array_equal(en.numpy(), er.numpy())
-    np.testing.assert_array_equal(vn.numpy(), vr.numpy())
+    if tables == "host":
+        np.testing.assert_array_equal(xn.numpy(), xr.numpy())
+        for a, b in zip(ir, in_):
+            np.testing.assert_array_equal(b.numpy(), a.numpy())
+        np.testing.assert_array_equal(en.numpy(), er.numpy())
+        np.testing.assert_array_equal(vn.numpy(), vr.numpy())
+    else:
+        for a, b in [(xr, xn), (er, en), (vr, vn)] + list(zip(ir, in_)):
+            assert rel_err(b.numpy(), a.numpy()) <= 1e-5
 
 
 def _sde_net(x, t):
@@ -111,7 +123,9 @@ def test_guided_diffusion_runner_runs_unchanged(product_device, kw):
     outs = []
     for tag, solver, dev in (("ref", A.reference_solver("guided"), "cpu"), ("b200", dpm_solver_b200, product_device)):
         _, sample_image = A.load_guided_runner(solver, tag)
-        me = A.guided_self(betas.to(dev), **kw)
+        # the schedule is built from `betas` where they live; on the host in both arms, so that the table (a log and
+        # a cumsum, :100-104) is the same one -- a device-side cumsum sums in another order
+        me = A.guided_self(betas, **kw)
         torch.manual_seed(5)                      # the runner draws the class labels with the global generator (:534-536)
         x, classes = sample_image(me, x_T.to(dev), A.guided_net, last=True,
                                   classifier=A.guided_classifier if use_classifier else None)

@@ -67,3 +67,65 @@ def test_sample_then_inverse_round_trip(oracle_backend):
     y = s.sample(x, steps=40, t_start=0.9, t_end=0.05, order=3, skip_type="logSNR")
     xr = s.inverse(y, steps=40, t_start=0.05, t_end=0.9, order=3, skip_type="logSNR")
     assert float((xr - x).abs().max() / x.abs().max()) < 1e-3
+
+
+# ---- the kernels' constant division (csrc/common.cuh: div_const) in exact rational arithmetic ----------------
+def _rn32(fr):
+    """Round a Fraction to the nearest float32 (ties to even), exactly."""
+    from fractions import Fraction
+    if fr == 0:
+        return np.float32(0.0)
+    c = np.float32(float(fr))                       # within one ulp of the answer (double rounding at worst)
+    cands = {float(c), float(np.nextafter(c, np.float32(np.inf))), float(np.nextafter(c, np.float32(-np.inf)))}
+    best = None
+    for v in cands:
+        err = abs(Fraction(v) - fr)
+        even = (np.float32(v).view(np.uint32) & 1) == 0
+        key = (err, 0 if even else 1)
+        if best is None or key < best[0]:
+            best = (key, v)
+    return np.float32(best[1])
+
+
+def test_two_step_constant_division_is_correctly_rounded():
+    """q0 = RN(x*r), then twice: e = x - q*d (one FMA), q = RN(q + e*r), with r = RN(1/d): equals RN(x/d) for every
+    divisor the kernels accept (recip_div_ok: |d| in 2^-20..2^20, significand not all ones). After the first
+    refinement the quotient is faithful, so the second residual is EXACT (asserted) -- the premise of Markstein's
+    theorem. Random and adversarial pairs: quotients next to rounding midpoints, divisors one ulp from a power of
+    two or from the excluded all-ones pattern."""
+    from fractions import Fraction
+    rng = np.random.default_rng(7)
+    ds = []
+    for _ in range(300):
+        ds.append(np.float32(rng.uniform(0.5, 2.0) * 2.0 ** rng.integers(-19, 19)))
+    for e in (-19, -3, 0, 1, 7, 18):
+        base = np.float32(2.0 ** e)
+        ds += [base, np.nextafter(base, np.float32(np.inf)), np.nextafter(np.nextafter(base, np.float32(0)), np.float32(0))]
+    checked = 0
+    for d in ds:
+        bits = int(np.float32(d).view(np.uint32))
+        if (bits & 0x7fffff) == 0x7fffff:
+            continue                                  # excluded on the host (IEEE path)
+        d = np.float32(d)
+        r = np.float32(1.0) / d                       # numpy's fp32 division is correctly rounded
+        assert _rn32(Fraction(1) / Fraction(float(d))) == r
+        xs = [np.float32(rng.standard_normal() * 10.0 ** rng.integers(-6, 6)) for _ in range(12)]
+        for _ in range(12):                           # quotients right at / next to a rounding midpoint
+            q = np.float32(rng.uniform(1.0, 2.0) * 2.0 ** rng.integers(-10, 10))
+            mid = (Fraction(float(q)) + Fraction(float(np.nextafter(q, np.float32(np.inf))))) / 2
+            x0 = _rn32(mid * Fraction(float(d)))
+            xs += [x0, np.nextafter(x0, np.float32(np.inf)), np.nextafter(x0, np.float32(-np.inf))]
+        for x in xs:
+            x = np.float32(x) * np.float32(rng.choice([-1.0, 1.0]))
+            if not (1e-25 < abs(float(x)) < 1e30):
+                continue
+            fx, fd, fr_ = Fraction(float(x)), Fraction(float(d)), Fraction(float(r))
+            q = _rn32(fx * fr_)
+            e = _rn32(fx - Fraction(float(q)) * fd)
+            q = _rn32(Fraction(float(q)) + Fraction(float(e)) * fr_)
+            e = _rn32(fx - Fraction(float(q)) * fd)
+            assert Fraction(float(e)) == fx - Fraction(float(q)) * fd, "the residual of a faithful quotient is exact"
+            q = _rn32(Fraction(float(q)) + Fraction(float(e)) * fr_)
+            assert q == _rn32(fx / fd), (float(x), float(d))
+            checked += 1
+    assert checked > 10000
