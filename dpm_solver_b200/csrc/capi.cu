@@ -346,6 +346,22 @@ int dpm_data_prediction(void* x0, const void* x, const void* eps, float alpha_t,
   return dpm_step(&d, stream);
 }
 
+int dpm_duplicate(void* out, const void* x, uint64_t n, int dtype, dpm_stream_t stream) {
+  if (n == 0) return DPM_OK;
+  if (out == nullptr || x == nullptr || !valid_dtype(dtype)) { set_error("duplicate: NULL tensor or bad dtype"); return DPM_ERR_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t bytes = n * (uint64_t)esize(dtype);
+  int r = launch_duplicate(out, x, bytes, st);
+  if (r == 1) {   // unaligned views: two plain device-to-device copies
+    cudaError_t e = cudaMemcpyAsync(out, x, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<char*>(out) + bytes, x, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("duplicate: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    return DPM_OK;
+  }
+  if (r != 0) return r;
+  return finish(st);
+}
+
 size_t dpm_dynamic_threshold_workspace(uint64_t n_samples, uint64_t per_sample) {
   return quantile_workspace_bytes(n_samples, per_sample);
 }

@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...);
 int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream);
 int launch_step_scalar(const KParams& p, cudaStream_t stream);
 int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream);
+int launch_duplicate(void* dst, const void* src, uint64_t bytes, cudaStream_t stream);
 int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q, float max_val,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t quantile_workspace_bytes(uint64_t n_samples, uint64_t per_sample);

@@ -241,6 +241,24 @@ class CudaBackend:
                      C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes))
         return out
 
+    def duplicate(self, x: torch.Tensor) -> torch.Tensor:
+        """torch.cat([x] * 2) (model_wrapper :326) -- one read, two bulk writes; layout of x kept."""
+        if x.dtype not in _DTYPE_CODE:
+            return torch.cat([x] * 2)
+        layout = self._layout(x)
+        if layout is None:
+            x, layout = x.contiguous(), "c"
+        shape = (2 * x.shape[0],) + tuple(x.shape[1:])
+        if layout == "cl":
+            out = torch.empty(shape, dtype=x.dtype, device=x.device,
+                              memory_format=torch.channels_last if x.dim() == 4 else torch.channels_last_3d)
+        else:
+            out = torch.empty(shape, dtype=x.dtype, device=x.device)
+        self._check(x, "x", x.device, x.numel(), layout=layout)
+        self._launch(x.device, self._lib.dpm_duplicate, C.c_void_p(out.data_ptr()), C.c_void_p(x.data_ptr()),
+                     C.c_uint64(x.numel()), C.c_int(_DTYPE_CODE[x.dtype]))
+        return out
+
     def launch_count(self) -> int:
         return int(self._lib.dpm_launch_count())
 

@@ -115,7 +115,7 @@ class WrappedModel:
             if not self.uses_cfg:
                 return RawOutput(self._call_model(x, t_continuous, cond=self.condition, t_input=t_input), None, param, 1.0)
             if x_in is None:
-                x_in = torch.cat([x] * 2)                      # :326 (the solver hands over a prebuilt one)
+                x_in = ops.backend().duplicate(x)              # cat([x] * 2) :326 (the solver hands over a prebuilt one)
             t_in = None if t_input is not None else torch.cat([t_continuous] * 2)
             out_u, out_c = self._call_model(x_in, t_in, cond=self._cond_in(), t_input=t_input).chunk(2)  # uncond first
             return RawOutput(out_c, out_u, param, float(self.guidance_scale))

@@ -189,6 +189,11 @@ DPM_API int dpm_singlestep_third_taylor_update(void* x_t, const void* x, const v
 DPM_API int dpm_cfg_combine(void* eps, const void* eps_uncond, const void* eps_cond, float scale,
                     uint64_t n, int dtype, dpm_stream_t stream);
 
+/* model_wrapper.model_fn classifier-free branch :326: x_in = torch.cat([x] * 2). out holds 2*n elements; x is read
+ * once and written to out[0, n) and out[n, 2n). (Inside the sampling loop dpm_step's out2 does this for free; this
+ * entry serves the first evaluation of a run.) */
+DPM_API int dpm_duplicate(void* out, const void* x, uint64_t n, int dtype, dpm_stream_t stream);
+
 /* DPM_Solver.data_prediction_fn :433-442 (without corrector when thr == NULL):
  * x0 = (x - sigma_t*eps)/alpha_t, then optional clamp(x0,-thr_b,thr_b)/thr_b. */
 DPM_API int dpm_data_prediction(void* x0, const void* x, const void* eps, float alpha_t, float sigma_t,

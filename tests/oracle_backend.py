@@ -142,6 +142,10 @@ class OracleBackend:
                 a.out2.copy_(out.reshape(a.out2.shape))
         return m_out, out
 
+    def duplicate(self, x):
+        self.launches += 1
+        return torch.cat([x] * 2)
+
     def error_norm(self, x_higher, x_lower, x_prev, atol, rtol):
         """dpm_solver_adaptive :999-1001 in numpy fp32."""
         self.launches += 1

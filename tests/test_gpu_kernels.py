@@ -399,3 +399,24 @@ def test_sample_with_channels_last_network(golden, cuda_backend):
     y = s.sample(x, steps=20, order=2)
     assert y.is_contiguous(memory_format=torch.channels_last)
     np.testing.assert_array_equal(y.cpu().numpy(), golden["samples"]["pp2m/y"])
+
+
+@pytest.mark.parametrize("sdt", [torch.float32, torch.bfloat16, torch.float16])
+def test_duplicate_equals_cat(cuda_backend, sdt):
+    """dpm_duplicate == torch.cat([x] * 2) (model_wrapper :326): tile-multiple, ragged, tiny, unaligned view, NaN/inf
+    payloads (a pure byte copy), channels_last."""
+    for shape in [(64, 4, 64, 64), (3, 4, 33, 17), (1, 1, 1, 8), (5, 3, 7, 7), (2, 1, 1, 1)]:
+        x = torch.randn(shape, device=DEV).to(sdt)
+        x.view(-1)[0] = float("nan")
+        x.view(-1)[-1] = float("inf")
+        got = cuda_backend.duplicate(x)
+        want = torch.cat([x] * 2)
+        assert got.shape == want.shape and got.dtype == want.dtype
+        assert torch.equal(got.view(torch.int16 if sdt != torch.float32 else torch.int32),
+                           want.view(torch.int16 if sdt != torch.float32 else torch.int32))
+    base = torch.randn(2 * 4 * 9 * 9 + 1, device=DEV).to(sdt)
+    v = base[1:].view(2, 4, 9, 9)                                  # misaligned view -> copy fallback
+    assert torch.equal(cuda_backend.duplicate(v), torch.cat([v] * 2))
+    xc = torch.randn(4, 8, 16, 16, device=DEV).to(sdt).contiguous(memory_format=torch.channels_last)
+    got = cuda_backend.duplicate(xc)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, torch.cat([xc] * 2))
