@@ -81,37 +81,86 @@ struct StageLayout {
   uint32_t bytes;                          // stage size
 };
 
+// shared-memory packet access by 32-bit shared-window address (no generic-pointer arithmetic in the loop)
+__device__ __forceinline__ void lds_pk32(Raw<float>& v, uint32_t a) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]) : "r"(a));
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+16];" : "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7]) : "r"(a));
+}
+template <typename T16>
+__device__ __forceinline__ void lds_pk32(Raw<T16>& v, uint32_t a) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]) : "r"(a));
+}
+__device__ __forceinline__ void sts_pk32(uint32_t a, const Raw<float>& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0+16], {%1,%2,%3,%4};" ::"r"(a), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7]) : "memory");
+}
+template <typename T16>
+__device__ __forceinline__ void sts_pk32(uint32_t a, const Raw<T16>& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g32(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kUnits = kTmaUnits;   // packets per thread per tile, compile time: both packets' LDS issue before the first use
+
+// Fast path only (launch_step_tma: fast_path_ok and no per-sample threshold): noise-parameterised network,
+// exact constant division. Everything that is uniform over a tile lives in uniform registers, computed once per
+// tile from 32-bit quantities (npk < 2^32): shared-window addresses of the stage's stream buffers, the tile's
+// packet count, the ring slot and its parity (counters, no division).
 template <typename TE, typename TS, int NE, int FORM>
 __global__ void __launch_bounds__(kTmaMaxThreads)
     k_step_tma(const __grid_constant__ KParams p, const __grid_constant__ StageLayout L,
-               const int stages, const int units) {
+               const int stages, const int /*units: compile time (kUnits)*/) {
   using Needs = FormNeeds<FORM>;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kMaxStages]
-  unsigned char* ring = smem + 128;
+  const uint32_t sbar = smem_u32(smem);           // [kMaxStages] mbarriers
+  const uint32_t sring = sbar + 128;
 
-  const int tid = threadIdx.x;
-  const uint32_t tile_pk = blockDim.x * units;
-  const uint32_t tile_el = tile_pk * kPacket;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nthr = blockDim.x;
+  const uint32_t tile_pk = nthr * kUnits;
   const uint32_t ntiles = (p.npk + tile_pk - 1) / tile_pk;
   const bool has_x = Needs::kX || (NE > 0 && p.use_xe);  // state slot: x, or xe when no update
   const bool sep_xe = (NE > 0) && p.use_xe && Needs::kX && !p.xe_is_x;  // extra slot: evaluation state
-  const bool clamp = (NE > 0) && (p.thr != nullptr);
   const bool has_mo = (NE > 0) && (p.m_out != nullptr);
+  const bool has_o2 = (FORM != DPM_FORM_NONE) && (p.out2 != nullptr);
   const char* gstate = static_cast<const char*>(Needs::kX ? p.x : p.xe);
+  constexpr uint32_t kBS = Traits<TS>::kBytes * kPacket, kBM = Traits<TE>::kBytes * kPacket;   // bytes per packet
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < stages; ++s) mbar_init(reinterpret_cast<uint64_t*>(smem) + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  auto issue_loads = [&](uint32_t tile, int s) {
-    const uint64_t e0 = (uint64_t)tile * tile_el;
-    uint64_t rem = (uint64_t)p.npk * kPacket - e0;
-    const uint32_t el = rem < tile_el ? (uint32_t)rem : tile_el;
-    const uint32_t bs = el * Traits<TS>::kBytes, bm = el * Traits<TE>::kBytes;
-    unsigned char* st = ring + (size_t)s * L.bytes;
+  auto issue_loads = [&](uint32_t tile, uint32_t s) {
+    const uint32_t pk0 = tile * tile_pk;
+    const uint32_t pk = min(p.npk - pk0, tile_pk);
+    const uint32_t bs = pk * kBS, bm = pk * kBM;
+    const uint64_t os = (uint64_t)pk0 * kBS, om = (uint64_t)pk0 * kBM;
+    const uint32_t st = sring + s * L.bytes, bar = sbar + s * 8;
     uint32_t tx = 0;
     if (has_x) tx += bs;
     if (sep_xe) tx += bs;
@@ -120,66 +169,77 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
     if (NE == 0) tx += bs;
     if (Needs::kM1) tx += bs;
     if (Needs::kM2) tx += bs;
-    mbar_expect_tx(&full[s], tx);
-    if (has_x) bulk_g2s(st + L.x, gstate + e0 * Traits<TS>::kBytes, bs, &full[s]);
-    if (sep_xe) bulk_g2s(st + L.xe, static_cast<const char*>(p.xe) + e0 * Traits<TS>::kBytes, bs, &full[s]);
-    if (NE >= 1) bulk_g2s(st + L.ec, static_cast<const char*>(p.ec) + e0 * Traits<TE>::kBytes, bm, &full[s]);
-    if (NE == 2) bulk_g2s(st + L.eu, static_cast<const char*>(p.eu) + e0 * Traits<TE>::kBytes, bm, &full[s]);
-    if (NE == 0) bulk_g2s(st + L.m0, static_cast<const char*>(p.m0) + e0 * Traits<TS>::kBytes, bs, &full[s]);
-    if (Needs::kM1) bulk_g2s(st + L.m1, static_cast<const char*>(p.m1) + e0 * Traits<TS>::kBytes, bs, &full[s]);
-    if (Needs::kM2) bulk_g2s(st + L.m2, static_cast<const char*>(p.m2) + e0 * Traits<TS>::kBytes, bs, &full[s]);
+    mbar_expect_tx32(bar, tx);
+    if (has_x) bulk_g2s32(st + L.x, gstate + os, bs, bar);
+    if (sep_xe) bulk_g2s32(st + L.xe, static_cast<const char*>(p.xe) + os, bs, bar);
+    if (NE >= 1) bulk_g2s32(st + L.ec, static_cast<const char*>(p.ec) + om, bm, bar);
+    if (NE == 2) bulk_g2s32(st + L.eu, static_cast<const char*>(p.eu) + om, bm, bar);
+    if (NE == 0) bulk_g2s32(st + L.m0, static_cast<const char*>(p.m0) + os, bs, bar);
+    if (Needs::kM1) bulk_g2s32(st + L.m1, static_cast<const char*>(p.m1) + os, bs, bar);
+    if (Needs::kM2) bulk_g2s32(st + L.m2, static_cast<const char*>(p.m2) + os, bs, bar);
   };
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      const uint64_t tile = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
-      if (tile < ntiles) issue_loads((uint32_t)tile, s);
+      const uint32_t tile = blockIdx.x + (uint32_t)s * gridDim.x;
+      if (tile < ntiles) issue_loads(tile, (uint32_t)s);
     }
   }
 
-  uint32_t it = 0;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int s = it % stages;
-    const uint32_t parity = (it / stages) & 1u;
-    unsigned char* st = ring + (size_t)s * L.bytes;
-    const uint64_t e0 = tile * tile_el;
-    const uint64_t rem = (uint64_t)p.npk * kPacket - e0;
-    const uint32_t el = rem < tile_el ? (uint32_t)rem : tile_el;
-    const uint32_t pk_here = el / kPacket;
+  uint32_t slot = 0, parity = 0;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t st = sring + slot * L.bytes;
+    const uint32_t pk0 = tile * tile_pk;
+    const uint32_t pk_here = min(p.npk - pk0, tile_pk);
 
-    mbar_wait(&full[s], parity);
+    mbar_wait32(sbar + slot * 8, parity);
 
-#pragma unroll 2
-    for (int u = 0; u < units; ++u) {
-      const uint32_t lp = u * blockDim.x + tid;  // packet inside the tile
+    // ---- load both packets of this thread, then compute ----
+    Raw<TS> rx[kUnits], rxe[kUnits], rm0[kUnits], rm1[kUnits], rm2[kUnits];
+    Raw<TE> rec[kUnits], reu[kUnits];
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+      const uint32_t lp = u * nthr + tid;  // packet inside the tile
       if (lp < pk_here) {
-        const uint32_t le = lp * kPacket;
+        if (has_x) lds_pk32(rx[u], st + L.x + lp * kBS);
+        if (sep_xe) lds_pk32(rxe[u], st + L.xe + lp * kBS);
+        if (Needs::kM1) lds_pk32(rm1[u], st + L.m1 + lp * kBS);
+        if (Needs::kM2) lds_pk32(rm2[u], st + L.m2 + lp * kBS);
+        if (NE >= 1) lds_pk32(rec[u], st + L.ec + lp * kBM);
+        if (NE == 2) lds_pk32(reu[u], st + L.eu + lp * kBM);
+        if (NE == 0) lds_pk32(rm0[u], st + L.m0 + lp * kBS);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+      const uint32_t lp = u * nthr + tid;
+      if (lp < pk_here) {
         float fx[8], fT[8], fm1[8], fm2[8], fo[8];
-        if (has_x) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.x) + le); unpack(r, fx); }
-        if (Needs::kM1) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m1) + le); unpack(r, fm1); }
-        if (Needs::kM2) { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m2) + le); unpack(r, fm2); }
+        if (has_x) unpack(rx[u], fx);
+        if (Needs::kM1) unpack(rm1[u], fm1);
+        if (Needs::kM2) unpack(rm2[u], fm2);
         if (NE > 0) {
           float fec[8], feu[8];
-          { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.ec) + le); unpack(r, fec); }
-          if (NE == 2) { Raw<TE> r; lds_pk(r, reinterpret_cast<const TE*>(st + L.eu) + le); unpack(r, feu); }
-          // per-sample threshold: uniform over the packet (fast path: per_sample % 8 == 0)
-          const float s_thr = clamp ? __ldg(p.thr + ((uint32_t)(e0 / kPacket) + lp) / p.pk_per_sample) : 1.f;   // packet index < 2^32 (npk)
+          unpack(rec[u], fec);
+          if (NE == 2) unpack(reu[u], feu);
           if (sep_xe) {
             float fxe[8];
-            { Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.xe) + le); unpack(r, fxe); }
-            fast_model8<NE>(p, fxe, fec, feu, clamp, s_thr, fT);
+            unpack(rxe[u], fxe);
+            fast_model8<NE>(p, fxe, fec, feu, false, 1.f, fT);
           } else {
-            fast_model8<NE>(p, fx, fec, feu, clamp, s_thr, fT);   // fx is only read when predict_x0 (then has_x)
+            fast_model8<NE>(p, fx, fec, feu, false, 1.f, fT);   // fx is only read when predict_x0 (then has_x)
           }
           Raw<TS> rmo;
           round_pack(rmo, fT);
-          if (has_mo) sts_pk(reinterpret_cast<TS*>(st + L.mo) + le, rmo);
+          if (has_mo) sts_pk32(st + L.mo + lp * kBS, rmo);
         } else {
-          Raw<TS> r; lds_pk(r, reinterpret_cast<const TS*>(st + L.m0) + le); unpack(r, fT);
+          unpack(rm0[u], fT);
         }
         if (FORM != DPM_FORM_NONE) {
           fast_update8<FORM>(p, fx, fT, fm1, fm2, fo);
-          Raw<TS> r; pack(r, fo); sts_pk(reinterpret_cast<TS*>(st + L.o) + le, r);
+          Raw<TS> r;
+          pack(r, fo);
+          sts_pk32(st + L.o + lp * kBS, r);
         }
       }
     }
@@ -187,16 +247,18 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
     if (tid == 0) bulk_wait_read(stages - 2);
     __syncthreads();
     if (tid == 0) {
-      const uint32_t bs = el * Traits<TS>::kBytes;
-      if (has_mo) bulk_s2g(static_cast<char*>(p.m_out) + e0 * Traits<TS>::kBytes, st + L.mo, bs);
+      const uint32_t bs = pk_here * kBS;
+      const uint64_t os = (uint64_t)pk0 * kBS;
+      if (has_mo) bulk_s2g32(static_cast<char*>(p.m_out) + os, st + L.mo, bs);
       if (FORM != DPM_FORM_NONE) {
-        bulk_s2g(static_cast<char*>(p.out) + e0 * Traits<TS>::kBytes, st + L.o, bs);
-        if (p.out2 != nullptr) bulk_s2g(static_cast<char*>(p.out2) + e0 * Traits<TS>::kBytes, st + L.o, bs);
+        bulk_s2g32(static_cast<char*>(p.out) + os, st + L.o, bs);
+        if (has_o2) bulk_s2g32(static_cast<char*>(p.out2) + os, st + L.o, bs);
       }
       bulk_commit();
-      const uint64_t next = tile + (uint64_t)stages * gridDim.x;
-      if (next < ntiles) issue_loads((uint32_t)next, s);
+      const uint32_t next = tile + (uint32_t)stages * gridDim.x;     // < 2^32: ntiles * (1 + stages) never gets near it
+      if (next < ntiles && next > tile) issue_loads(next, slot);
     }
+    if (++slot == (uint32_t)stages) { slot = 0; parity ^= 1u; }
   }
   if (tid == 0) bulk_wait_all();
 }
@@ -240,7 +302,8 @@ static TmaKernel pick_tma(int md, int sd, int ne, int form) {
 }
 
 int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
-  if (!fast_path_ok(p)) return 1;   // other parameterisations / non-refinable divisors: the direct variant's generic kernels
+  if (!fast_path_ok(p) || p.thr != nullptr) return 1;   // other parameterisations, non-refinable divisors, per-sample
+                                                        // thresholds: the direct variant
   const bool need_x = p.form != DPM_FORM_NONE;
   TmaKernel k = pick_tma(p.model_dtype, p.state_dtype, p.n_model, p.form);
   if (k == nullptr) return 1;
@@ -264,8 +327,7 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
 
   StageLayout L;
   int threads = 0, stages = 0;
-  int units = kTmaUnits;
-  if (const char* e = getenv("DPM_TMA_UNITS")) { const int v = atoi(e); if (v >= 1 && v <= 8) units = v; }
+  const int units = kTmaUnits;   // compile-time constant of the kernel
   // tile = threads * units packets. Default 256 threads x 2 CTAs/SM (512 resident threads):
   // the sweep in profiles/ shows two stages at that size beat more, smaller stages; the tile only
   // shrinks when two stages of it do not fit.

@@ -259,11 +259,89 @@ class CudaBackend:
                      C.c_uint64(x.numel()), C.c_int(_DTYPE_CODE[x.dtype]))
         return out
 
+    def prepare(self, a: StepArgs) -> Optional["PreparedStep"]:
+        """Freeze the descriptor of a launch whose scalars will not change (one step of a cached coefficient plan):
+        later launches of the same step only patch the tensor pointers. None if the launch is not eligible."""
+        return PreparedStep.build(self, a)
+
     def launch_count(self) -> int:
         return int(self._lib.dpm_launch_count())
 
     def set_tuning(self, variant: int = 2, threads: int = 0, ctas_per_sm: int = 0) -> None:
         _lib.check(self._lib.dpm_set_tuning(variant, threads, ctas_per_sm))
+
+
+class PreparedStep:
+    """One step of a cached coefficient plan, ready to launch: a filled `dpm_step_desc` whose scalar fields are final.
+    `launch()` validates the tensors of this call with a handful of attribute reads (dtype, size, density, device),
+    patches the pointers, allocates the outputs and calls the C-ABI -- the per-step host path of a steady-state
+    sample() loop (tools/host_overhead.py). Anything unusual (other layout, dtype, device, size) returns None and the
+    caller takes the general path (`CudaBackend.step`)."""
+
+    __slots__ = ("be", "d", "ref_d", "fn", "n", "dev", "dev_index", "sdt", "mdt", "shape", "need_out", "need_m",
+                 "fields", "dup")
+
+    @staticmethod
+    def build(be: "CudaBackend", a: StepArgs) -> Optional["PreparedStep"]:
+        if a.thr is not None or a.raw_round or a.out is not None and a.out2 is None:
+            return None
+        ref = a.reference_tensor()
+        if not ref.is_contiguous():
+            return None
+        for t in a.state_tensors() + a.model_tensors():
+            if not t.is_contiguous() or t.device != ref.device:
+                return None
+        d, keep, ref, sdt, layout = be._fill(a)
+        if layout != "c":
+            return None
+        self = PreparedStep()
+        self.be, self.d, self.ref_d, self.fn = be, d, C.byref(d), be._lib.dpm_step
+        self.n, self.dev, self.dev_index = ref.numel(), ref.device, ref.device.index
+        self.sdt = sdt
+        self.mdt = a.e_cond.dtype if a.e_cond is not None else sdt
+        self.shape = tuple(ref.shape)
+        self.need_out = a.form != FORM_NONE
+        self.need_m = a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE)
+        self.dup = a.out2 is not None
+        # (descriptor field, StepArgs attribute, expected dtype) of every input tensor this launch reads
+        self.fields = tuple((f, name, self.mdt if name in ("e_cond", "e_uncond") else sdt)
+                            for f, name in (("x", "x"), ("xe", "xe"), ("m0", "m0"), ("m1", "m1"), ("m2", "m2"),
+                                            ("e_cond", "e_cond"), ("e_uncond", "e_uncond"))
+                            if getattr(a, name) is not None)
+        return self
+
+    def launch(self, tensors: dict):
+        """tensors: StepArgs attribute name -> tensor for every input of the frozen launch. Returns
+        (m_out, out, x_in) -- x_in is the doubled CFG batch when the step was prepared with a second output copy --
+        or None when a tensor does not look like the ones the step was prepared for."""
+        d, n, dev = self.d, self.n, self.dev
+        for f, name, dt in self.fields:
+            t = tensors.get(name)
+            if t is None or t.dtype is not dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
+                return None
+            setattr(d, f, t.data_ptr())
+        m_out = out = x_in = None
+        if self.need_m:
+            m_out = torch.empty(self.shape, dtype=self.sdt, device=dev)
+            d.m_out = m_out.data_ptr()
+        if self.need_out:
+            if self.dup:
+                x_in = torch.empty((2 * self.shape[0],) + self.shape[1:], dtype=self.sdt, device=dev)
+                out = x_in[:self.shape[0]]
+                d.out = x_in.data_ptr()
+                d.out2 = x_in.data_ptr() + n * x_in.element_size()
+            else:
+                out = torch.empty(self.shape, dtype=self.sdt, device=dev)
+                d.out = out.data_ptr()
+        idx = self.dev_index
+        if torch.cuda.current_device() == idx:
+            rc = self.fn(self.ref_d, _raw_stream(idx))
+        else:
+            with torch.cuda.device(dev):
+                rc = self.fn(self.ref_d, _raw_stream(idx))
+        if rc != 0:
+            _lib.check(rc)
+        return m_out, out, x_in
 
 
 _backend = None

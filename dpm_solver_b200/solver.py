@@ -254,6 +254,8 @@ class DPM_Solver:
         self.plan_broadcast = bool(plan_broadcast)
         self.reference_rounding = bool(reference_rounding)
         self._rr_run = 0     # raw_round of the buffered values of the run in flight (reference_rounding)
+        self._prep_cache = {}   # frozen launch descriptors of cached plan steps (ops.PreparedStep)
+        self._prep_on = False
 
     @staticmethod
     def _x0_hook(fn):
@@ -368,6 +370,11 @@ class DPM_Solver:
         return (getattr(ns, "schedule", None), getattr(ns, "beta_0", None), getattr(ns, "beta_1", None),
                 getattr(ns, "T", None))
 
+    def _plan_id(self, key):
+        """Hashable identity of a cached plan (schedule + algorithm + sampling arguments): prepared launches are
+        keyed by it, so a changed schedule or argument never meets a stale descriptor."""
+        return (self._schedule_key(), self.algorithm_type, self.plan_broadcast) + key
+
     def _host_plan(self, key, build):
         """Coefficient plan of a run, cached per (schedule, algorithm, sampling arguments): repeated
         sample() calls with the same configuration (serving) skip the host scalar work entirely."""
@@ -467,12 +474,31 @@ class DPM_Solver:
                                    w4=co.w4)
 
     def _post_model(self, raw: RawOutput, xe, t_dev, alsig, co: Optional[P.Coeffs] = None, x=None,
-                    m1=None, m2=None, want_m: bool = True, dup_out: bool = False, x0: Optional[bool] = None):
+                    m1=None, m2=None, want_m: bool = True, dup_out: bool = False, x0: Optional[bool] = None,
+                    slot=None):
         """The fused post-model step: buffered value from `raw` (+ optional update `co`).
 
         Returns (m_new, x_next). Falls back to two launches only when a user-supplied
-        `correcting_x0_fn` must see the materialised x0 (:440-441)."""
+        `correcting_x0_fn` must see the materialised x0 (:440-441).
+
+        `slot` names a step of a CACHED coefficient plan (sample() loops): its launch descriptor is frozen after
+        the first run (ops.PreparedStep) and later runs only patch tensor pointers -- the steady-state host path."""
         be = ops.backend()
+        pkey = None
+        if slot is not None and self._prep_on:
+            pkey = (slot, raw.param, raw.guidance, raw.e_uncond is None, raw.e_cond.dtype, xe.dtype, tuple(xe.shape),
+                    want_m, dup_out)
+            prep = self._prep_cache.get(pkey)
+            if prep is not None:
+                r = prep.launch({"x": x, "xe": xe, "m0": raw.e_cond, "m1": m1, "m2": m2, "e_cond": raw.e_cond,
+                                 "e_uncond": raw.e_uncond})
+                if r is not None:
+                    m_new, x_next, x_in = r
+                    if x_in is not None:
+                        self._xin_pair = (x_next, x_in)
+                    if m_new is None and prep.d.n_model == 0:
+                        m_new = raw.e_cond                  # pure update on the raw noise: it IS the buffered value
+                    return m_new, x_next
         x0 = self._pp if x0 is None else x0          # buffered value: x0 (dpmsolver++ / data_prediction_fn) or eps
         sd = xe.dtype if xe is not None else (x.dtype if x is not None else raw.e_cond.dtype)
         custom_fix = x0 and self.correcting_x0_fn is not None and not self._dynamic_thresholding
@@ -492,7 +518,8 @@ class DPM_Solver:
             co = self._rr_coeffs(co, code)
         if not self._needs_conversion(raw, sd, x0):
             m_new = raw.e_cond if ops.CudaBackend._layout(raw.e_cond) is not None else raw.e_cond.contiguous()
-            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr) if co is not None else None
+            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr, pkey=pkey if m_new is raw.e_cond else None) \
+                if co is not None else None
             return m_new, x_next
         a = self._conv_args(raw, xe, alsig, sd, x0)
         if x0 and self._dynamic_thresholding:
@@ -515,7 +542,19 @@ class DPM_Solver:
         m_new, x_next = be.step(a)
         if dup is not None:
             self._xin_pair = (x_next, dup[0])
+        if pkey is not None and not a.per_sample:
+            self._remember(pkey, a, dup)
         return m_new, x_next
+
+    def _remember(self, pkey, a: StepArgs, dup=None) -> None:
+        """Freeze the launch that just ran as the prepared form of its plan step."""
+        if dup is not None:
+            a.out, a.out2 = dup[1], dup[2]
+        prep = ops.backend().prepare(a)
+        if prep is not None:
+            if len(self._prep_cache) >= 512:
+                self._prep_cache.clear()
+            self._prep_cache[pkey] = prep
 
     @staticmethod
     def _state_like(t, sd):
@@ -530,7 +569,7 @@ class DPM_Solver:
         a.w0, a.w1, a.w2, a.w3, a.w4 = co.w0, co.w1, co.w2, co.w3, co.w4
         a.c0_on_old = co.c0_on_old
 
-    def _pure_update(self, co: P.Coeffs, x, m0, m1=None, m2=None, rr: Optional[int] = None):
+    def _pure_update(self, co: P.Coeffs, x, m0, m1=None, m2=None, rr: Optional[int] = None, pkey=None):
         if rr is None:
             # directly called update methods: buffers handed over in one 16-bit type are raw outputs
             rr = 0
@@ -541,7 +580,10 @@ class DPM_Solver:
         a = StepArgs(n_model=0, m0=self._state_like(m0, x.dtype), state_dtype=x.dtype, raw_round=rr)
         self._fill_update(a, co, x, None if m1 is None else self._state_like(m1, x.dtype),
                           None if m2 is None else self._state_like(m2, x.dtype))
-        return ops.backend().step(a)[1]
+        out = ops.backend().step(a)[1]
+        if pkey is not None and not rr:
+            self._remember(pkey, a)
+        return out
 
     # -- reference API: model functions ---------------------------------------------------------
     def dynamic_thresholding_fn(self, x0, t):
@@ -646,7 +688,7 @@ class DPM_Solver:
 
     def _run_singlestep(self, x, sp: P.SinglestepPlan, model_s=None, model_s1=None, keep=False,
                         times_dev: Optional[List[torch.Tensor]] = None, alsig=None, t_inputs=None,
-                        dup_last: bool = False):
+                        dup_last: bool = False, slot=None):
         """Execute one singlestep update: one fused launch per model evaluation.
 
         Stage j converts the network output evaluated at (x_j, times[j]) and, in the same kernel,
@@ -681,7 +723,8 @@ class DPM_Solver:
                     m_new, _ = self._post_model(raw, xe, td[j], als[j])
                 else:
                     m_new, x_next = self._post_model(raw, xe, td[j], als[j], co, x, m1, m2, want_m=want,
-                                                     dup_out=(not last) or dup_last)
+                                                     dup_out=(not last) or dup_last,
+                                                     slot=None if slot is None else slot + (j,))
                 ms[j] = m_new
             xe = x_next
         return x_next, ms
@@ -858,6 +901,9 @@ class DPM_Solver:
         ns = self.noise_schedule
         self._xin_pair = None
         self._rr_run = 0
+        # prepared launches: the CUDA executor, no python-side x0 hook, no 16-bit reference-rounding mode
+        self._prep_on = (hasattr(ops.backend(), "prepare") and not self.reference_rounding
+                         and (self.correcting_x0_fn is None or self._dynamic_thresholding))
         with torch.no_grad():
             x = self._state(x)
             sd = x.dtype
@@ -901,7 +947,8 @@ class DPM_Solver:
                     m2 = older[-2] if co.order >= 3 else None
                     want = order >= 2 and step < steps
                     m_new, x_new = self._post_model(raw, xe, ts_dev[step - 1], alsig[step - 1], co, x,
-                                                    m1, m2, want_m=want, dup_out=step < steps)
+                                                    m1, m2, want_m=want, dup_out=step < steps,
+                                                    slot=(self._plan_id(key), step))
                     x = x_new
                     t = ts_dev[step]
                     if self.correcting_xt_fn is not None:
@@ -966,7 +1013,7 @@ class DPM_Solver:
                     td = [all_dev[k + j:k + j + 1] for j in range(nt)]
                     x, _ = self._run_singlestep(x, sp, times_dev=td, alsig=alsig[k:k + nt],
                                                 t_inputs=None if tin is None else [tin[k + j] for j in range(nt)],
-                                                dup_last=step + 1 < len(plans))
+                                                dup_last=step + 1 < len(plans), slot=(self._plan_id(key), step))
                     k += nt
                     if self.correcting_xt_fn is not None:
                         x = self._state_like(self.correcting_xt_fn(x, outer_dev[step + 1], step), sd)

@@ -170,3 +170,29 @@ def test_capture_api(golden, cuda_backend):
     assert torch.equal(y2, s.sample(x * 0.25, steps=20, order=2))
     with pytest.raises(ValueError):
         s.capture(x, method="adaptive")
+
+
+@pytest.mark.parametrize("name", ["pp2m", "pp3m", "eps3s_cfg", "pp2m_cfg_v", "eps2m_score", "pp3s_taylor"])
+def test_prepared_steps_replay_equals_first_run(golden, cuda_backend, name):
+    """Second and later sample() calls of a solver launch frozen descriptors (ops.PreparedStep: pointers patched,
+    no per-step argument marshalling). They must reproduce the first (general-path) run and the reference golden
+    bit for bit, follow a changed input, and fall back cleanly when the input looks different (other batch size)."""
+    case = CASES[name]
+    y1, _, _, s = run_product_case(case, device="cuda:0", return_solver=True)
+    assert s._prep_cache, "no launch was frozen"
+    x = __import__("cases").seeded(case["shape"], case["seed"]).cuda()
+    kw = dict(steps=case["steps"], order=case["order"], skip_type=case["skip_type"], method=case["method"],
+              lower_order_final=case.get("lower_order_final", True), denoise_to_zero=case.get("denoise_to_zero", False),
+              solver_type=case.get("solver_type", "dpmsolver"), t_end=case.get("t_end"))
+    before = cuda_backend.launch_count()
+    y2 = s.sample(x, **kw)
+    assert cuda_backend.launch_count() > before
+    assert torch.equal(y2, y1)
+    np.testing.assert_array_equal(y2.cpu().numpy(), golden["samples"][f"{name}/y"])
+    y3 = s.sample(x * 0.5, **kw)                                 # new values, same descriptors
+    s._prep_cache.clear()
+    assert torch.equal(y3, s.sample(x * 0.5, **kw))             # == the general path
+    if not case.get("cfg"):                                      # (the CFG cases carry per-sample conditions)
+        y4 = s.sample(x[:1], **kw)                               # other batch size: other descriptors
+        s._prep_cache.clear()
+        assert torch.equal(y4, s.sample(x[:1], **kw))

@@ -35,6 +35,8 @@ ncu_quantile)
   done ;;
 sweep)
   timeout 1200 bash tools/inloop_sweep.sh c2 c3 > /dev/null 2>&1; cat gpurun_out/inloop_sweep.txt ;;
+l2probe)
+  timeout 300 python tools/l2_group_probe.py > gpurun_out/l2_group_probe.txt 2>&1; cat gpurun_out/l2_group_probe.txt ;;
 latency)
   timeout 600 python tools/host_overhead.py > gpurun_out/host_overhead.txt 2>&1; cat gpurun_out/host_overhead.txt ;;
 *) echo "unknown stage $stage" ;;

@@ -11,7 +11,7 @@ WL=${@:-c2 c3}
 for w in $WL; do
   for cfg in "2 0 0" "2 256 2" "2 256 3" "2 128 4" "2 128 6" "1 256 3" "1 256 4" "1 128 6" "1 128 8" "4 256 1" "4 128 2"; do
     set -- $cfg
-    line=$(DPM_TMA_UNITS=$1 timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-extras --threads $2 --ctas $3 2>/dev/null | tail -1)
+    line=$(timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-extras --threads $2 --ctas $3 2>/dev/null | tail -1)
     python - "$w" "$1" "$2" "$3" "$line" >> $OUT <<'PY'
 import json, sys
 w, u, t, c, line = sys.argv[1:6]
