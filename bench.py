@@ -379,6 +379,38 @@ def make_timed_backend():
             self.records.append((key, self._bytes(a, m_out, out), e0, e1))
             return m_out, out
 
+        def prepare(self, a):
+            """Frozen launches (ops.PreparedStep) bypass step(): wrap them so that they are timed too."""
+            prep = super().prepare(a)
+            if prep is None:
+                return None
+            n = a.reference_tensor().numel()
+            es = a.reference_tensor().element_size() if a.state_dtype is None else torch.empty((), dtype=a.state_dtype).element_size()
+            seen, tot = set(), 0
+            for t in (a.x, a.xe, a.m0, a.m1, a.m2, a.e_cond, a.e_uncond):
+                if t is not None and t.data_ptr() not in seen:
+                    seen.add(t.data_ptr())
+                    tot += n * t.element_size()
+            tot += n * es * (int(prep.need_m) + int(prep.need_out) * (2 if prep.dup else 1))
+            key = f"{FORM_NAMES[a.form]}|n_model={a.n_model}|m_out={int(prep.need_m)}"
+            outer = self
+
+            class TimedPrepared:
+                d = prep.d
+
+                def launch(self, tensors):
+                    if not outer.recording:
+                        return prep.launch(tensors)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = prep.launch(tensors)
+                    e1.record()
+                    if r is not None:
+                        outer.records.append((key, tot, e0, e1))
+                    return r
+
+            return TimedPrepared()
+
         def dynamic_threshold(self, a, q, max_val):
             if not self.recording:
                 return super().dynamic_threshold(a, q, max_val)

@@ -9,8 +9,9 @@ The arithmetic runs in hand-written CUDA kernels behind a C-ABI shared library
 PyTorch fallback: CUDA tensors only, and a missing library raises.
 """
 from .schedule import NoiseScheduleVP, expand_dims, interpolate_fn
+from .diffedit import DiffEditCorrector
 from .solver import DPM_Solver, WrappedModel, model_wrapper
 
 __version__ = "0.1.0"
 __all__ = ["NoiseScheduleVP", "model_wrapper", "DPM_Solver", "WrappedModel", "interpolate_fn",
-           "expand_dims"]
+           "expand_dims", "DiffEditCorrector"]

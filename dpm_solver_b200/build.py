@@ -25,7 +25,10 @@ OUT_DIR = PKG / "lib"
 BUILD_DIR = PKG / "build"
 LIB_NAME = "libdpmsolver_b200.so"
 
-SOURCES = ["capi.cu", "step_direct.cu", "step_tma.cu", "quantile.cu", "adaptive.cu"]
+SOURCES = ["capi.cu", "step_direct.cu", "step_tma.cu", "quantile.cu", "adaptive.cu", "philox.cu"]
+# philox.cu embeds curand's Box-Muller, which must round exactly like the copy inside torch's randn kernel: it is
+# compiled with nvcc's default fma contraction and spells the reference's unfused chain with __fmul_rn/__fadd_rn
+FMAD_DEFAULT = {"philox.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -66,7 +69,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
 
     def compile_one(src: str) -> Path:
         obj = objdir / (src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-I", str(CSRC), "-c",
+        flags = [f for f in NVCC_FLAGS if not (src in FMAD_DEFAULT and f == "-fmad=false")]
+        cmd = [nvcc, *ARCH, *flags, *extra, "-I", str(INCLUDE), "-I", str(CSRC), "-c",
                str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

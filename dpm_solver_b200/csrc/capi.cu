@@ -362,6 +362,30 @@ int dpm_duplicate(void* out, const void* x, uint64_t n, int dtype, dpm_stream_t 
   return finish(st);
 }
 
+int dpm_philox_policy(uint64_t numel, uint32_t* grid, uint64_t* counter_offset) {
+  if (grid == nullptr || counter_offset == nullptr) { set_error("philox policy: NULL output"); return DPM_ERR_ARG; }
+  philox_policy(numel, grid, counter_offset);
+  return DPM_OK;
+}
+
+int dpm_add_noise_philox(void* xt, const void* x, uint64_t n, int t_count, const float* alpha_t, const float* sigma_t,
+                         uint64_t seed, uint64_t offset, int x_dtype, int out_dtype, dpm_stream_t stream) {
+  if (n == 0 || t_count == 0) return DPM_OK;
+  if (!xt || !x || !alpha_t || !sigma_t || !valid_dtype(x_dtype) || !valid_dtype(out_dtype)) { set_error("add_noise: NULL argument or bad dtype"); return DPM_ERR_ARG; }
+  int rc = launch_noise_philox(xt, x, nullptr, nullptr, 0, n, t_count, alpha_t, sigma_t, seed, offset, x_dtype, out_dtype,
+                               static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
+}
+
+int dpm_diffedit_corrector(void* out, const void* x, const void* x0, const float* mask, uint64_t mask_n, uint64_t n,
+                           float alpha_t, float sigma_t, uint64_t seed, uint64_t offset, int dtype, dpm_stream_t stream) {
+  if (n == 0) return DPM_OK;
+  if (!out || !x || !x0 || !mask || mask_n == 0 || n % mask_n != 0 || !valid_dtype(dtype)) { set_error("corrector: NULL argument, bad dtype or a mask that does not tile x"); return DPM_ERR_ARG; }
+  int rc = launch_noise_philox(out, x0, x, mask, mask_n, n, 1, &alpha_t, &sigma_t, seed, offset, dtype, dtype,
+                               static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
+}
+
 size_t dpm_dynamic_threshold_workspace(uint64_t n_samples, uint64_t per_sample) {
   return quantile_workspace_bytes(n_samples, per_sample);
 }

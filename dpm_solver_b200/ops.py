@@ -259,6 +259,54 @@ class CudaBackend:
                      C.c_uint64(x.numel()), C.c_int(_DTYPE_CODE[x.dtype]))
         return out
 
+    # -- noise drawn inside the kernel (torch.randn-compatible Philox; csrc/philox.cu) ----------------------
+    @staticmethod
+    def _philox_state(device, numel: int, lib, generator=None):
+        """(seed, offset) of the torch CUDA generator for a randn of `numel` elements, advancing it exactly as
+        ATen's normal_ kernel would (so later torch RNG calls see the state they would have seen)."""
+        gen = generator if generator is not None else torch.cuda.default_generators[device.index]
+        grid, inc = C.c_uint32(0), C.c_uint64(0)
+        _lib.check(lib.dpm_philox_policy(C.c_uint64(numel), C.byref(grid), C.byref(inc)))
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        gen.set_offset(offset + inc.value)
+        return seed, offset
+
+    def add_noise_philox(self, x: torch.Tensor, alphas, sigmas, out_dtype, generator=None) -> torch.Tensor:
+        """[T, *x.shape] = alpha_i * x + sigma_i * randn, the noise generated in registers (reference :1023-1026)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("dpm_solver_b200: in-kernel noise reads the generator state on the host; pass `noise=` under CUDA-graph capture")
+        x = self._check(x, "x", x.device, x.numel())
+        T = len(alphas)
+        out = torch.empty((T,) + tuple(x.shape), dtype=out_dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            seed, offset = self._philox_state(x.device, T * x.numel(), self._lib, generator)
+        fa = (C.c_float * T)(*alphas)
+        fs = (C.c_float * T)(*sigmas)
+        self._launch(x.device, self._lib.dpm_add_noise_philox, C.c_void_p(out.data_ptr()), C.c_void_p(x.data_ptr()),
+                     C.c_uint64(x.numel()), C.c_int(T), fa, fs, C.c_uint64(seed), C.c_uint64(offset),
+                     C.c_int(_DTYPE_CODE[x.dtype]), C.c_int(_DTYPE_CODE[out_dtype]))
+        return out
+
+    def diffedit_corrector(self, x, x0, mask, alpha: float, sigma: float, generator=None) -> torch.Tensor:
+        """x*mask + (1 - mask)*(alpha*x0 + sigma*randn_like(x0)) in one launch (diffedit_inpaint.ipynb corrector_fn)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("dpm_solver_b200: in-kernel noise reads the generator state on the host; not capturable")
+        n = x.numel()
+        x = self._check(x, "x", x.device, n)
+        x0 = self._check(x0, "x0", x.device, n, x.dtype)
+        if mask.dtype != torch.float32 or not mask.is_contiguous() or n % max(mask.numel(), 1) \
+                or tuple(mask.shape) != tuple(x.shape[x.dim() - mask.dim():]):
+            mask = mask.to(torch.float32).expand(x.shape).contiguous()        # any other broadcast: materialise
+        if mask.device != x.device:
+            raise RuntimeError("dpm_solver_b200: `mask` must live on the device of x")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            seed, offset = self._philox_state(x.device, n, self._lib, generator)
+        self._launch(x.device, self._lib.dpm_diffedit_corrector, C.c_void_p(out.data_ptr()), C.c_void_p(x.data_ptr()),
+                     C.c_void_p(x0.data_ptr()), C.c_void_p(mask.data_ptr()), C.c_uint64(mask.numel()), C.c_uint64(n),
+                     C.c_float(alpha), C.c_float(sigma), C.c_uint64(seed), C.c_uint64(offset), C.c_int(_DTYPE_CODE[x.dtype]))
+        return out
+
     def prepare(self, a: StepArgs) -> Optional["PreparedStep"]:
         """Freeze the descriptor of a launch whose scalars will not change (one step of a cached coefficient plan):
         later launches of the same step only patch the tensor pointers. None if the launch is not eligible."""
@@ -278,8 +326,11 @@ class PreparedStep:
     sample() loop (tools/host_overhead.py). Anything unusual (other layout, dtype, device, size) returns None and the
     caller takes the general path (`CudaBackend.step`)."""
 
-    __slots__ = ("be", "d", "ref_d", "fn", "n", "dev", "dev_index", "sdt", "mdt", "shape", "need_out", "need_m",
-                 "fields", "dup")
+    __slots__ = ("be", "d", "ref_d", "fn", "n", "dev", "dev_index", "sdt", "mdt", "shape", "shape2", "need_out",
+                 "need_m", "fields", "dup", "ptrs", "esize")
+
+    # index of every pointer field inside struct dpm_step_desc (its first 11 members are pointers)
+    _PTR = {"x": 0, "xe": 1, "m0": 2, "m1": 3, "m2": 4, "m_out": 5, "out": 6, "out2": 7, "e_cond": 8, "e_uncond": 9}
 
     @staticmethod
     def build(be: "CudaBackend", a: StepArgs) -> Optional["PreparedStep"]:
@@ -300,40 +351,43 @@ class PreparedStep:
         self.sdt = sdt
         self.mdt = a.e_cond.dtype if a.e_cond is not None else sdt
         self.shape = tuple(ref.shape)
+        self.shape2 = (2 * self.shape[0],) + self.shape[1:]
+        self.esize = torch.empty((), dtype=sdt).element_size()
+        # the descriptor's pointer members as a uint64 array: patching one is a numpy scalar store, not a ctypes setattr
+        import numpy as np
+        self.ptrs = np.frombuffer((C.c_char * C.sizeof(d)).from_buffer(d), dtype=np.uint64, count=11)
         self.need_out = a.form != FORM_NONE
         self.need_m = a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE)
         self.dup = a.out2 is not None
         # (descriptor field, StepArgs attribute, expected dtype) of every input tensor this launch reads
-        self.fields = tuple((f, name, self.mdt if name in ("e_cond", "e_uncond") else sdt)
-                            for f, name in (("x", "x"), ("xe", "xe"), ("m0", "m0"), ("m1", "m1"), ("m2", "m2"),
-                                            ("e_cond", "e_cond"), ("e_uncond", "e_uncond"))
-                            if getattr(a, name) is not None)
+        self.fields = tuple((self._PTR[name], name, self.mdt if name in ("e_cond", "e_uncond") else sdt)
+                            for name in ("x", "xe", "m0", "m1", "m2", "e_cond", "e_uncond") if getattr(a, name) is not None)
         return self
 
     def launch(self, tensors: dict):
         """tensors: StepArgs attribute name -> tensor for every input of the frozen launch. Returns
         (m_out, out, x_in) -- x_in is the doubled CFG batch when the step was prepared with a second output copy --
         or None when a tensor does not look like the ones the step was prepared for."""
-        d, n, dev = self.d, self.n, self.dev
+        n, dev, idx, ptrs = self.n, self.dev, self.dev_index, self.ptrs
         for f, name, dt in self.fields:
             t = tensors.get(name)
-            if t is None or t.dtype is not dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
+            if t is None or t.dtype is not dt or t.numel() != n or not t.is_contiguous() or t.get_device() != idx:
                 return None
-            setattr(d, f, t.data_ptr())
+            ptrs[f] = t.data_ptr()
         m_out = out = x_in = None
         if self.need_m:
             m_out = torch.empty(self.shape, dtype=self.sdt, device=dev)
-            d.m_out = m_out.data_ptr()
+            ptrs[5] = m_out.data_ptr()
         if self.need_out:
             if self.dup:
-                x_in = torch.empty((2 * self.shape[0],) + self.shape[1:], dtype=self.sdt, device=dev)
+                x_in = torch.empty(self.shape2, dtype=self.sdt, device=dev)
                 out = x_in[:self.shape[0]]
-                d.out = x_in.data_ptr()
-                d.out2 = x_in.data_ptr() + n * x_in.element_size()
+                base = x_in.data_ptr()
+                ptrs[6] = base
+                ptrs[7] = base + n * self.esize
             else:
                 out = torch.empty(self.shape, dtype=self.sdt, device=dev)
-                d.out = out.data_ptr()
-        idx = self.dev_index
+                ptrs[6] = out.data_ptr()
         if torch.cuda.current_device() == idx:
             rc = self.fn(self.ref_d, _raw_stream(idx))
         else:

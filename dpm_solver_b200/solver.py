@@ -829,6 +829,14 @@ class DPM_Solver:
         """xt = alpha_t * x + sigma_t * noise for every t in `t` -> (t_size, batch, *shape)."""
         th = P._cpu(t)
         alpha_t, sigma_t = self.noise_schedule.marginal_alpha(th), self.noise_schedule.marginal_std(th)
+        be = ops.backend()
+        if noise is None and x.is_cuda and hasattr(be, "add_noise_philox") and th.shape[0] <= 16 \
+                and x.dtype in ops.SUPPORTED_DTYPES and not torch.cuda.is_current_stream_capturing():
+            # the noise never touches HBM: drawn in registers by the generator torch.randn would have used, same
+            # (seed, offset) -> same values, the torch generator advanced as randn would have (csrc/philox.cu)
+            xs = self._state_like(x, x.dtype)
+            outs = be.add_noise_philox(xs, alpha_t.tolist(), sigma_t.tolist(), self._sdtype(x))
+            return outs[0] if th.shape[0] == 1 else outs
         if noise is None:
             noise = torch.randn((th.shape[0], *x.shape), device=x.device)
         # result dtype: the reference's fp32 (t_size,1,..) coefficient tensors promote a 16-bit x to fp32 (:1026)
@@ -934,6 +942,7 @@ class DPM_Solver:
                 # model evaluation 0, then one fused launch per step:
                 #   m_{i} = convert(net(x_i, t_i));  x_{i+1} = update(x_i, m_i, m_{i-1}, m_{i-2})
                 step = 0
+                pid = self._plan_id(key)
                 raw = self._evaluate(x, ts_dev[0], None if tin is None else tin[0])
                 xe = x
                 if self.correcting_xt_fn is not None:
@@ -948,7 +957,7 @@ class DPM_Solver:
                     want = order >= 2 and step < steps
                     m_new, x_new = self._post_model(raw, xe, ts_dev[step - 1], alsig[step - 1], co, x,
                                                     m1, m2, want_m=want, dup_out=step < steps,
-                                                    slot=(self._plan_id(key), step))
+                                                    slot=(pid, step))
                     x = x_new
                     t = ts_dev[step]
                     if self.correcting_xt_fn is not None:
@@ -1008,12 +1017,13 @@ class DPM_Solver:
                 all_dev, outer_dev = (packed_dev[:n_eval], packed_dev[n_eval:]) if plans else (None, None)
                 k = 0
                 step = 0
+                pid = self._plan_id(key)
                 for step, sp in enumerate(plans):
                     nt = len(sp.times)
                     td = [all_dev[k + j:k + j + 1] for j in range(nt)]
                     x, _ = self._run_singlestep(x, sp, times_dev=td, alsig=alsig[k:k + nt],
                                                 t_inputs=None if tin is None else [tin[k + j] for j in range(nt)],
-                                                dup_last=step + 1 < len(plans), slot=(self._plan_id(key), step))
+                                                dup_last=step + 1 < len(plans), slot=(pid, step))
                     k += nt
                     if self.correcting_xt_fn is not None:
                         x = self._state_like(self.correcting_xt_fn(x, outer_dev[step + 1], step), sd)

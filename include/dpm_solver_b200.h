@@ -200,6 +200,27 @@ DPM_API int dpm_data_prediction(void* x0, const void* x, const void* eps, float 
                         const float* thr, uint64_t per_sample, uint64_t n, int dtype,
                         dpm_stream_t stream);
 
+/* ---- noise drawn inside the kernel (torch.randn-compatible Philox) ------------------------------------------
+ * ATen's launch policy for a randn of `numel` elements on the current device: the virtual grid the kernels below
+ * replay, and the amount the caller must advance the torch CUDA generator's philox offset by afterwards. */
+DPM_API int dpm_philox_policy(uint64_t numel, uint32_t* grid, uint64_t* counter_offset);
+
+/* DPM_Solver.add_noise(x, t, noise=None) :1012-1030 with the noise generated in registers:
+ *   xt[i] = alpha_t[i]*x + sigma_t[i]*randn[i],  i < t_count <= 16 (alpha_t, sigma_t: HOST arrays),  xt: [t_count, n].
+ * (seed, offset) = the torch CUDA generator's state; for that state the result equals
+ * torch.randn((t_count, n)) followed by the reference's three eager ops, bit for bit. x_dtype -> out_dtype: the
+ * reference's promotion (16-bit x, fp32 result) or 16-bit storage. */
+DPM_API int dpm_add_noise_philox(void* xt, const void* x, uint64_t n, int t_count, const float* alpha_t,
+                                 const float* sigma_t, uint64_t seed, uint64_t offset, int x_dtype, int out_dtype,
+                                 dpm_stream_t stream);
+
+/* DiffEdit corrector (examples/stable-diffusion/scripts/diffedit_inpaint.ipynb corrector_fn + sampler.py:92-96):
+ *   out = x*mask + (1 - mask)*(alpha_t*x0 + sigma_t*randn_like(x0)),  one launch, noise in registers.
+ * mask: fp32, mask_n elements, broadcast over the leading dimensions of x (n % mask_n == 0). */
+DPM_API int dpm_diffedit_corrector(void* out, const void* x, const void* x0, const float* mask, uint64_t mask_n,
+                                   uint64_t n, float alpha_t, float sigma_t, uint64_t seed, uint64_t offset,
+                                   int dtype, dpm_stream_t stream);
+
 /* DPM_Solver.dynamic_thresholding_fn :416-423, first half: per-sample
  * s_b = max(quantile(|x0_b|, q), max_val) with torch.quantile's linear interpolation between
  * the two adjacent order statistics (rank arithmetic in fp32). x0 is recomputed on the fly from

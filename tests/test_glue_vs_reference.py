@@ -199,3 +199,84 @@ def test_capture_with_denoise_to_zero(cuda_backend):
     nr = _sched(ref)
     yr = ref.DPM_Solver(ref.model_wrapper(exact_net, nr), nr).sample(x.cpu(), **kw)
     np.testing.assert_array_equal(eager.cpu().numpy(), yr.numpy())
+
+
+# ---- in-kernel noise: add_noise(noise=None) and the DiffEdit corrector ------------------------------
+def _notebook_corrector(sampler, init_latent, mask):
+    """diffedit_inpaint.ipynb, `corrector_fn`, verbatim."""
+    def corrector_fn(x, t, step):
+        ratio = sampler.time_to_ratio(t)
+        stochastic_intermediate = sampler.stochastic_encode(init_latent, ratio)
+        x = x * mask + (1 - mask) * stochastic_intermediate
+        return x
+    return corrector_fn
+
+
+def test_diffedit_corrector_matches_the_notebook_on_the_host_executor(oracle_backend):
+    """DiffEditCorrector == the notebook's corrector_fn on top of the unmodified SD adapter, same CPU generator state."""
+    import adapters as A
+    import dpm_solver_b200 as new
+    mod = A.load_sd_adapter(A.reference_solver("sd"), "diffedit_ref", "cpu")
+    sampler = mod.DPMSolverSampler(A.StubLatentDiffusion("cpu"))
+    x0, x = seeded((1, 4, 16, 16), 3), seeded((1, 4, 16, 16), 4)
+    mask = (seeded((16, 16), 5) > 0).float()
+    ns = new.NoiseScheduleVP("discrete", alphas_cumprod=sampler.alphas_cumprod)
+    fused = new.DiffEditCorrector(ns, x0, mask, time_fn=lambda t: sampler.ratio_to_time(sampler.time_to_ratio(t)))
+    ref_fn = _notebook_corrector(sampler, x0, mask)
+    for step, tv in enumerate([0.9, 0.5, 0.05]):
+        t = torch.tensor(tv)
+        torch.manual_seed(100 + step)
+        want = ref_fn(x, t, step)
+        torch.manual_seed(100 + step)
+        got = fused(x, t, step)
+        np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,times", [((2, 4, 64, 64), [0.5]), ((3, 3, 17, 5), [0.3, 0.8, 0.05]), ((700, 4, 64, 64), [0.6])])
+def test_add_noise_draws_torch_randn_in_the_kernel(cuda_backend, shape, times):
+    """add_noise(noise=None): the noise is generated in registers by curand's Philox exactly as torch.randn would
+    have (same seed and offset -> same normals, generator advanced identically), then alpha*x + sigma*noise."""
+    import dpm_solver_b200 as new
+    s = new.DPM_Solver(None, _sched(new))
+    x = seeded(shape, 8).cuda()
+    t = torch.tensor(times, device="cuda")
+    torch.manual_seed(1234)
+    torch.randn(5, device="cuda")                                     # a non-zero philox offset
+    state = torch.cuda.get_rng_state()
+    before = cuda_backend.launch_count()
+    got = s.add_noise(x, t)
+    assert cuda_backend.launch_count() == before + 1                  # ONE launch, no randn kernel, no noise tensor
+    after_fused = torch.cuda.default_generators[0].get_offset()
+    torch.cuda.set_rng_state(state)
+    noise = torch.randn((len(times), *x.shape), device="cuda")       # what the reference draws (:1024)
+    assert torch.cuda.default_generators[0].get_offset() == after_fused
+    want = s.add_noise(x, t, noise=noise)                             # explicit-noise path (bit-exact vs the reference)
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+    ref = ref_loader.load("dpm_solver_pytorch")
+    want_cpu = ref.DPM_Solver(None, _sched(ref)).add_noise(x.cpu(), t.cpu(), noise=noise.cpu())
+    np.testing.assert_array_equal(got.cpu().numpy(), want_cpu.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sdt", [torch.float32, torch.bfloat16])
+def test_diffedit_corrector_fused_kernel(cuda_backend, sdt):
+    """One launch == x*mask + (1-mask)*(alpha*x0 + sigma*randn) with torch's own normals for the generator state."""
+    import dpm_solver_b200 as new
+    ns = _sched(new)
+    x0, x = seeded((2, 4, 64, 64), 3).cuda().to(sdt), seeded((2, 4, 64, 64), 4).cuda().to(sdt)
+    mask = (seeded((64, 64), 5) > 0).float().cuda()
+    fused = new.DiffEditCorrector(ns, x0, mask)
+    t = torch.tensor([0.4], device="cuda")
+    torch.manual_seed(77)
+    state = torch.cuda.get_rng_state()
+    before = cuda_backend.launch_count()
+    got = fused(x, t, 0)
+    assert cuda_backend.launch_count() == before + 1
+    torch.cuda.set_rng_state(state)
+    noise = torch.randn((1, *x0.shape), device="cuda")
+    al, sg = float(ns.marginal_alpha(t.cpu())), float(ns.marginal_std(t.cpu()))
+    inter = (torch.tensor(al) * x0.float().cpu() + torch.tensor(sg) * noise[0].cpu())
+    want = x.float().cpu() * mask.cpu() + (1 - mask.cpu()) * inter
+    np.testing.assert_array_equal(got.float().cpu().numpy(), want.to(sdt).float().numpy())

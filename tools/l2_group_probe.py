@@ -21,7 +21,12 @@ from dpm_solver_b200.ops import StepArgs  # noqa: E402
 be = ops.CudaBackend()
 ps = 3 * 256 * 256
 Gs = [int(v) for v in sys.argv[1:]] or [8, 16, 24, 32, 48, 64, 96]
-flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+flush = torch.zeros(256 << 20, dtype=torch.float32, device="cuda")     # 1 GiB, evicted by READING it: no dirty lines left behind
+sink = torch.zeros(1, device="cuda")
+
+
+def evict():
+    sink.copy_(flush.sum().reshape(1))
 for G in Gs:
     n = G * ps
     mk = lambda: torch.randn(n, device="cuda")
@@ -37,10 +42,10 @@ for G in Gs:
     for mode in ("cold", "after_quantile"):
         ts = []
         for rep in range(5):
-            flush.fill_(rep)                       # evict everything
+            evict()
             thr = be.dynamic_threshold(args(), 0.995, 1.0)
             if mode == "cold":
-                flush.fill_(rep + 7)
+                evict()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             be.step(args(thr))
