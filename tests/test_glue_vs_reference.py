@@ -276,7 +276,8 @@ def test_diffedit_corrector_fused_kernel(cuda_backend, sdt):
     assert cuda_backend.launch_count() == before + 1
     torch.cuda.set_rng_state(state)
     noise = torch.randn((1, *x0.shape), device="cuda")
-    al, sg = float(ns.marginal_alpha(t.cpu())), float(ns.marginal_std(t.cpu()))
+    te = t.cpu().to(sdt).float()            # stochastic_encode rebuilds the label in the latent's dtype (sampler.py:94)
+    al, sg = float(ns.marginal_alpha(te)), float(ns.marginal_std(te))
     inter = (torch.tensor(al) * x0.float().cpu() + torch.tensor(sg) * noise[0].cpu())
     want = x.float().cpu() * mask.cpu() + (1 - mask.cpu()) * inter
     np.testing.assert_array_equal(got.float().cpu().numpy(), want.to(sdt).float().numpy())

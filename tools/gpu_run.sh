@@ -35,6 +35,8 @@ ncu_quantile)
   done ;;
 sweep)
   timeout 1200 bash tools/inloop_sweep.sh c2 c3 > /dev/null 2>&1; cat gpurun_out/inloop_sweep.txt ;;
+l2ncu)
+  timeout 400 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct -k regex:k_step_direct --csv --log-file gpurun_out/l2_ncu.csv python tools/l2_group_probe.py 16 24 32 48 64 > gpurun_out/l2_ncu.log 2>&1; python tools/l2_ncu_digest.py gpurun_out/l2_ncu.csv ;;
 l2probe)
   timeout 300 python tools/l2_group_probe.py > gpurun_out/l2_group_probe.txt 2>&1; cat gpurun_out/l2_group_probe.txt ;;
 latency)
