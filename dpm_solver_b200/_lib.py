@@ -34,6 +34,19 @@ class StepDesc(C.Structure):
         ("a", C.c_float), ("c0", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
         ("w0", C.c_float), ("w1", C.c_float), ("w2", C.c_float), ("w3", C.c_float),
         ("w4", C.c_float),
+        ("dev_coef", C.c_void_p),
+    ]
+
+
+class AdaptiveCtl(C.Structure):
+    """struct dpm_adaptive_ctl"""
+    _fields_ = [
+        ("schedule_kind", C.c_int32), ("table_len", C.c_int32),
+        ("t_array", C.c_void_p), ("log_alpha_array", C.c_void_p), ("log_alpha_flipped", C.c_void_p), ("t_flipped", C.c_void_p),
+        ("beta_0", C.c_float), ("beta_1_minus_beta_0", C.c_float), ("inv_total_N", C.c_float),
+        ("discrete_time_input", C.c_int32), ("order", C.c_int32), ("predict_x0", C.c_int32), ("taylor", C.c_int32),
+        ("t_0", C.c_float), ("theta", C.c_float), ("t_err", C.c_float),
+        ("state", C.c_void_p), ("coef", C.c_void_p), ("times", C.c_void_p), ("error", C.c_void_p),
     ]
 
 
@@ -61,6 +74,10 @@ PROTOTYPES = {
     "dpm_data_prediction": (C.c_int, [_vp, _vp, _vp, _f, _f, _vp, _u64, _u64, _i, _vp]),
     "dpm_dynamic_threshold_workspace": (C.c_size_t, [_u64, _u64]),
     "dpm_dynamic_threshold": (C.c_int, [_vp, C.POINTER(StepDesc), _f, _f, _vp, C.c_size_t, _vp]),
+    "dpm_adaptive_init": (C.c_int, [C.POINTER(AdaptiveCtl), _f, _f, _vp]),
+    "dpm_adaptive_plan": (C.c_int, [C.POINTER(AdaptiveCtl), _vp]),
+    "dpm_adaptive_decide": (C.c_int, [C.POINTER(AdaptiveCtl), _vp]),
+    "dpm_select_copy": (C.c_int, [_vp, _vp, _vp, _u64, _vp]),
     "dpm_adaptive_error_workspace": (C.c_size_t, [_u64, _u64]),
     "dpm_adaptive_error": (C.c_int, [_vp, _vp, _vp, _vp, _f, _f, _u64, _u64, _i, _vp, C.c_size_t, _vp]),
 }

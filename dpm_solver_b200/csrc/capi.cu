@@ -169,6 +169,7 @@ static int build_params(const dpm_step_desc* d, KParams* kp, Needs* nd, bool for
   kp->raw_round = d->raw_round;
   kp->r_w4 = need_w4 && ok ? 1.0f / d->w4 : 0.f;
   kp->fast_div = ok ? 1 : 0;
+  kp->dev_coef = for_quantile ? nullptr : d->dev_coef;
   return DPM_OK;
 }
 
@@ -220,7 +221,8 @@ static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   Tuning t{g_variant.load(), g_threads.load(), g_ctas.load()};
 
   bool body_done = false;
-  if (p.npk > 0 && all_aligned(p, nd) && p.raw_round == 0) {   // reference-rounding mode: generic kernel only
+  if (p.npk > 0 && all_aligned(p, nd) && p.raw_round == 0 && p.dev_coef == nullptr) {   // reference-rounding mode and
+                                                                                       // device-side scalars: generic kernel only
     int r = 1;
     // small launches (a few tiles per SM) gain nothing from the ring; auto keeps them direct
     // fp32 state: direct 256-bit loads sit at the HBM roofline already (fewer instructions per
@@ -404,6 +406,25 @@ int dpm_dynamic_threshold(float* s_out, const dpm_step_desc* desc, float q, floa
                        static_cast<cudaStream_t>(stream));
   if (rc != DPM_OK) return rc;
   return finish(static_cast<cudaStream_t>(stream));
+}
+
+int dpm_adaptive_init(const dpm_adaptive_ctl* ctl, float t_T, float h_init, dpm_stream_t stream) {
+  int rc = launch_adaptive_init(ctl, t_T, h_init, static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
+}
+int dpm_adaptive_plan(const dpm_adaptive_ctl* ctl, dpm_stream_t stream) {
+  int rc = launch_adaptive_plan(ctl, static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
+}
+int dpm_adaptive_decide(const dpm_adaptive_ctl* ctl, dpm_stream_t stream) {
+  int rc = launch_adaptive_decide(ctl, static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
+}
+int dpm_select_copy(void* dst, const void* src, const float* state, uint64_t bytes, dpm_stream_t stream) {
+  if (bytes == 0) return DPM_OK;
+  if (!dst || !src || !state) { set_error("select copy: NULL argument"); return DPM_ERR_ARG; }
+  int rc = launch_select_copy(dst, src, state, bytes, static_cast<cudaStream_t>(stream));
+  return rc != DPM_OK ? rc : finish(static_cast<cudaStream_t>(stream));
 }
 
 size_t dpm_adaptive_error_workspace(uint64_t n, uint64_t per_sample) {

@@ -56,6 +56,7 @@ struct KParams {
   int32_t raw_round;
   float r_w4;
   int32_t fast_div;
+  const float* dev_coef;   // optional: scalars read from device memory (dpm_step_desc.dev_coef); generic kernel only
 };
 
 // ---- storage types ------------------------------------------------------------------------

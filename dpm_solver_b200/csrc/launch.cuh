@@ -29,6 +29,10 @@ void philox_policy(uint64_t numel, uint32_t* grid, uint64_t* counter_offset);
 int launch_noise_philox(void* out, const void* x, const void* xt, const float* mask, uint64_t mask_n, uint64_t n,
                         int t_count, const float* alpha, const float* sigma, uint64_t seed, uint64_t offset,
                         int x_dtype, int out_dtype, cudaStream_t stream);
+int launch_adaptive_init(const dpm_adaptive_ctl* a, float t_T, float h_init, cudaStream_t stream);
+int launch_adaptive_plan(const dpm_adaptive_ctl* a, cudaStream_t stream);
+int launch_adaptive_decide(const dpm_adaptive_ctl* a, cudaStream_t stream);
+int launch_select_copy(void* dst, const void* src, const float* state, uint64_t bytes, cudaStream_t stream);
 int launch_duplicate(void* dst, const void* src, uint64_t bytes, cudaStream_t stream);
 int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q, float max_val,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);

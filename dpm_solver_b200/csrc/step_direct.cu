@@ -141,7 +141,16 @@ __global__ void __launch_bounds__(kMaxThreads)
 // ---- fully generic element-wise kernel: any dtype mix, any alignment, tails ------------------
 // RND = true: reference-rounding mode (common.cuh); the only kernel that implements it so far.
 template <bool RND>
-__global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256) k_step_scalar(const __grid_constant__ KParams pc) {
+  KParams p = pc;
+  if (pc.dev_coef != nullptr) {
+    // scalars produced on the device by the adaptive controller (adaptive_ctl.cu: CO_* layout)
+    const float* c = pc.dev_coef;
+    p.a = c[0]; p.c0 = c[1]; p.c1 = c[2]; p.c2 = c[3];
+    p.w0 = c[4]; p.w1 = c[5]; p.w2 = c[6]; p.w3 = c[7]; p.w4 = c[8];
+    p.alpha_e = c[9]; p.sigma_e = c[10];
+    p.fast_div = 0;
+  }
   const int sd = p.state_dtype, md = p.model_dtype;
   const bool need_x = p.form != DPM_FORM_NONE;
   const bool need_m1 = p.form == DPM_FORM_LIN2 || p.form == DPM_FORM_LIN3 ||

@@ -314,12 +314,14 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   const bool m2 = p.form == DPM_FORM_LIN3 || p.form == DPM_FORM_MS3 || p.form == DPM_FORM_SS3T;
   const int n_streams = (need_x || (p.n_model > 0 && p.use_xe)) + sep_xe + p.n_model + (p.n_model == 0) + m1 + m2 +
                         (p.n_model > 0 && p.m_out != nullptr) + need_x;
-  // 16-bit sweeps (profiles/r01_sweep2.jsonl, r01_tma_units.txt): <= 4 streams run best as 256 threads x 3
-  // CTAs/SM, more as 256 x 2. 128 x 4 wins the isolated back-to-back sweep for 5-6 streams by ~3% but
-  // LOSES 4-7% inside the sampling loop (bench.py c2/c3, interleaved with the model's kernels), so the
-  // in-loop result decides.
+  // Launch shape, decided INSIDE the sampling loop (tools/inloop_sweep.sh; profiles/r02_inloop_sweep.txt): launches
+  // with <= 4 shared-memory streams run best as 256 threads x 3 CTAs/SM, 5 streams as 256 x 2 (c2: 622 GElem/s vs
+  // 604 for 512 x 1); when the tile is also stored twice (out2: 6 HBM streams, the CFG steps of c3) one 512-thread
+  // CTA per SM with two 80 KB stages wins (c3: 464 vs 451 GElem/s).
   int def_threads = 256, def_ctas = 2;
+  const int hbm_streams = n_streams + (need_x && p.out2 != nullptr);
   if (ss == 2 && ms == 2 && n_streams <= 4) def_ctas = 3;
+  else if (ss == 2 && ms == 2 && hbm_streams >= 6) { def_threads = 512; def_ctas = 1; }
   const int ctas = t.ctas_per_sm > 0 ? t.ctas_per_sm : def_ctas;
   // smem budget per CTA: the SM's 228 KB hold `ctas` CTAs (1 KB reserved per CTA)
   const size_t per_cta = (size_t)(228 * 1024) / ctas - 1024;
@@ -331,7 +333,7 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   // tile = threads * units packets. Default 256 threads x 2 CTAs/SM (512 resident threads):
   // the sweep in profiles/ shows two stages at that size beat more, smaller stages; the tile only
   // shrinks when two stages of it do not fit.
-  const int cand[4] = {t.threads > 0 ? t.threads : def_threads, 128, 64, 32};
+  const int cand[4] = {t.threads > 0 ? t.threads : def_threads, t.threads > 0 || def_threads > 256 ? 256 : 128, 64, 32};
   for (int c = 0; c < (t.threads > 0 ? 1 : 4); ++c) {
     const uint32_t tile_el = (uint32_t)cand[c] * units * kPacket;
     uint32_t o = 0;

@@ -56,6 +56,7 @@ class StepArgs:
     out2: Optional[torch.Tensor] = None    # optional second copy of x_t (doubled CFG batch)
     m_out: Optional[torch.Tensor] = None
     raw_round: int = 0                # reference-rounding mode (dpm_step_desc.raw_round); 0 = off
+    coef_dev: Optional[torch.Tensor] = None   # 16 fp32 on the device: the launch reads its scalars there (dev_coef)
 
     def state_tensors(self):
         return [t for t in (self.x, self.xe, self.m0, self.m1, self.m2) if t is not None]
@@ -164,6 +165,12 @@ class CudaBackend:
         d.guidance, d.alpha_e, d.sigma_e = a.guidance, a.alpha_e, a.sigma_e
         d.a, d.c0, d.c1, d.c2 = a.a, a.c0, a.c1, a.c2
         d.w0, d.w1, d.w2, d.w3, d.w4 = a.w0, a.w1, a.w2, a.w3, a.w4
+        if a.coef_dev is not None:
+            cd = a.coef_dev
+            if not cd.is_cuda or cd.dtype != torch.float32 or cd.numel() < 16 or not cd.is_contiguous() or cd.device != dev:
+                raise TypeError("dpm_solver_b200: `coef_dev` must be 16 contiguous fp32 values on the tensors' device")
+            keep.append(cd)
+            d.dev_coef = cd.data_ptr()
         return d, keep, ref, sdt, layout
 
     def _new_like(self, ref, sdt, layout):
@@ -227,12 +234,13 @@ class CudaBackend:
             return s, hdr
         return s
 
-    def error_norm(self, x_higher, x_lower, x_prev, atol: float, rtol: float) -> torch.Tensor:
+    def error_norm(self, x_higher, x_lower, x_prev, atol: float, rtol: float, out=None) -> torch.Tensor:
         """E of dpm_solver_adaptive (:999-1001) as a device fp32 tensor of shape (1,)."""
         n, dev = x_higher.numel(), x_higher.device
         ts = [self._check(t, w, dev, n, x_higher.dtype) for t, w in ((x_higher, "x_higher"), (x_lower, "x_lower"), (x_prev, "x_prev"))]
         per_sample = n // x_higher.shape[0]
-        out = torch.empty(1, dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(1, dtype=torch.float32, device=dev)
         ws_bytes = int(self._lib.dpm_adaptive_error_workspace(n, per_sample))
         ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
         self._launch(dev, self._lib.dpm_adaptive_error, C.c_void_p(out.data_ptr()), C.c_void_p(ts[0].data_ptr()),
@@ -258,6 +266,10 @@ class CudaBackend:
         self._launch(x.device, self._lib.dpm_duplicate, C.c_void_p(out.data_ptr()), C.c_void_p(x.data_ptr()),
                      C.c_uint64(x.numel()), C.c_int(_DTYPE_CODE[x.dtype]))
         return out
+
+    def adaptive_controller(self, ns, device, **kw) -> "AdaptiveController":
+        """Device-resident step-size controller of dpm_solver_adaptive (csrc/adaptive_ctl.cu)."""
+        return AdaptiveController(self, ns, device, **kw)
 
     # -- noise drawn inside the kernel (torch.randn-compatible Philox; csrc/philox.cu) ----------------------
     @staticmethod
@@ -317,6 +329,72 @@ class CudaBackend:
 
     def set_tuning(self, variant: int = 2, threads: int = 0, ctas_per_sm: int = 0) -> None:
         _lib.check(self._lib.dpm_set_tuning(variant, threads, ctas_per_sm))
+
+
+class AdaptiveController:
+    """State, coefficient blocks and time labels of dpm_solver_adaptive (:956-1010) in device memory, plus the three
+    tiny kernels that advance them (dpm_adaptive_init / _plan / _decide) and the conditional commit
+    (dpm_select_copy). `read()` is the only host synchronisation."""
+
+    SUPPORTED = ("discrete", "linear")
+
+    def __init__(self, be: "CudaBackend", ns, device, order: int, predict_x0: bool, taylor: bool, t_0: float,
+                 theta: float, t_err: float, discrete_input: bool):
+        if ns.schedule not in self.SUPPORTED:
+            raise ValueError("the device controller supports the 'discrete' and 'linear' schedules")
+        self.be, self.dev = be, torch.device(device)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.state = torch.zeros(16, **f32)
+        self.coef = torch.zeros(4, 16, **f32)
+        self.times = torch.zeros(6, **f32)
+        self.E = torch.zeros(1, **f32)
+        c = self.ctl = _lib.AdaptiveCtl()
+        self._keep = []
+        if ns.schedule == "discrete":
+            tabs = ns._table(self.dev)[:4]
+            self._keep = [t.to(torch.float32).contiguous() for t in tabs]
+            c.schedule_kind, c.table_len = 0, self._keep[0].numel()
+            c.t_array, c.log_alpha_array, c.log_alpha_flipped, c.t_flipped = (t.data_ptr() for t in self._keep)
+            c.inv_total_N = 1. / ns.total_N
+        else:
+            c.schedule_kind, c.table_len = 1, 0
+            c.beta_0, c.beta_1_minus_beta_0 = ns.beta_0, ns.beta_1 - ns.beta_0
+            c.inv_total_N = 1. / ns.total_N
+        c.discrete_time_input = int(bool(discrete_input))
+        c.order, c.predict_x0, c.taylor = order, int(bool(predict_x0)), int(bool(taylor))
+        c.t_0, c.theta, c.t_err = t_0, theta, t_err
+        c.state, c.coef, c.times, c.error = (t.data_ptr() for t in (self.state, self.coef, self.times, self.E))
+        self._ref = C.byref(c)
+
+    def init(self, t_T: float, h_init: float) -> None:
+        self.be._launch(self.dev, self.be._lib.dpm_adaptive_init, self._ref, C.c_float(t_T), C.c_float(h_init))
+
+    def plan(self) -> None:
+        self.be._launch(self.dev, self.be._lib.dpm_adaptive_plan, self._ref)
+
+    def decide(self) -> None:
+        self.be._launch(self.dev, self.be._lib.dpm_adaptive_decide, self._ref)
+
+    def select_copy(self, dst: torch.Tensor, src: torch.Tensor) -> None:
+        """dst <- src iff the last decide() accepted the step."""
+        if dst.shape != src.shape or dst.dtype != src.dtype or not dst.is_contiguous() or not src.is_contiguous():
+            raise ValueError("select_copy: dense tensors of one shape and dtype")
+        self.be._launch(self.dev, self.be._lib.dpm_select_copy, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()),
+                        C.c_void_p(self.state.data_ptr()), C.c_uint64(dst.numel() * dst.element_size()))
+
+    def block(self, i: int) -> torch.Tensor:
+        return self.coef[i]
+
+    def time(self, j: int) -> torch.Tensor:
+        return self.times[j:j + 1]
+
+    def input_time(self, j: int) -> torch.Tensor:
+        return self.times[3 + j:4 + j]
+
+    def read(self):
+        """(done, nfe, iterations): the one device->host read of a chunk."""
+        st = self.state.cpu().view(torch.int32)
+        return int(st[6]), int(st[5]), int(st[8])
 
 
 class PreparedStep:

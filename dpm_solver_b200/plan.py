@@ -39,6 +39,7 @@ class Coeffs:
     c0_on_old: bool = False
     order: int = 1
     r_tensor: int = 0   # SS3T: bit 0 / 1 = r1 / r2 came as tensors (matters to reference_rounding only)
+    dev: Optional[torch.Tensor] = None   # scalars live in this device block instead (on-device adaptive controller)
 
 
 def _cpu(t: torch.Tensor) -> torch.Tensor:

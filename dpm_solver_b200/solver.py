@@ -31,6 +31,8 @@ from .ops import StepArgs
 
 __all__ = ["model_wrapper", "DPM_Solver", "WrappedModel"]
 
+_DEV = object()     # marker: the scalars of this evaluation live in device memory (on-device adaptive controller)
+
 
 # =================================================================================================
 # model_wrapper
@@ -441,7 +443,10 @@ class DPM_Solver:
                      e_uncond=raw.e_uncond, param=raw.param, guidance=raw.guidance,
                      predict_x0=x0, state_dtype=sdtype)
         if x0 or raw.param != PARAM_NOISE:
-            a.alpha_e, a.sigma_e = alsig if isinstance(alsig, tuple) else self._alpha_sigma(alsig)
+            if alsig is _DEV:
+                pass        # (alpha_t, sigma_t) arrive with the launch's device coefficient block (StepArgs.coef_dev)
+            else:
+                a.alpha_e, a.sigma_e = alsig if isinstance(alsig, tuple) else self._alpha_sigma(alsig)
             a.xe = xe
         return a
 
@@ -522,6 +527,10 @@ class DPM_Solver:
                 if co is not None else None
             return m_new, x_next
         a = self._conv_args(raw, xe, alsig, sd, x0)
+        if alsig is _DEV:
+            if co is None or co.dev is None:
+                raise RuntimeError("device-side scalars need the coefficient block of the consuming launch")
+            a.coef_dev = co.dev
         if x0 and self._dynamic_thresholding:
             a.per_sample = xe.numel() // xe.shape[0]
             a.thr = be.dynamic_threshold(a, float(self.dynamic_thresholding_ratio),
@@ -565,6 +574,8 @@ class DPM_Solver:
     @staticmethod
     def _fill_update(a: StepArgs, co: P.Coeffs, x, m1, m2) -> None:
         a.form, a.x, a.m1, a.m2 = co.form, x, m1, m2
+        if co.dev is not None:
+            a.coef_dev = co.dev
         a.a, a.c0, a.c1, a.c2 = co.a, co.c0, co.c1, co.c2
         a.w0, a.w1, a.w2, a.w3, a.w4 = co.w0, co.w1, co.w2, co.w3, co.w4
         a.c0_on_old = co.c0_on_old
@@ -777,6 +788,13 @@ class DPM_Solver:
         ns = self.noise_schedule
         x = self._state(x)
         device = x.device
+        if order not in (2, 3):
+            raise ValueError("For adaptive step size solver, order must be 2 or 3, got {}".format(order))
+        if solver_type not in ['dpmsolver', 'taylor']:
+            raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+        if self._device_controller_ok(x):
+            return self._adaptive_on_device(x, order, t_T, t_0, h_init, atol, rtol, theta, t_err, solver_type)
+        # host controller (schedules / options the device controller does not cover, and the CPU test executor):
         # the controller's scalars live on the host (fp32, reference op order); the network receives
         # device time labels, uploaded once per iteration
         s = t_T * torch.ones((1,))
@@ -821,6 +839,72 @@ class DPM_Solver:
                 lambda_s = ns.marginal_lambda(s)
             h = torch.min(theta * h * torch.float_power(E, -1. / order).float(), lambda_0 - lambda_s)
             nfe += order
+        print('adaptive solver nfe', nfe)
+        return x
+
+    adaptive_controller = "device"   # "host": the reference's per-iteration host decision (one sync per iteration)
+    adaptive_chunk = 4               # iterations enqueued between two reads of the device-side `done` flag
+
+    def _device_controller_ok(self, x) -> bool:
+        be = ops.backend()
+        w = self._wrapped
+        return (self.adaptive_controller == "device" and hasattr(be, "adaptive_controller") and x.is_cuda
+                and getattr(self.noise_schedule, "schedule", None) in ops.AdaptiveController.SUPPORTED
+                and not self._dynamic_thresholding        # the quantile call takes alpha_t, sigma_t by value
+                and not self.reference_rounding
+                and not (isinstance(w, WrappedModel) and not w.fusable)      # classifier guidance: model_fn needs host scalars
+                and not torch.cuda.is_current_stream_capturing())
+
+    def _adaptive_on_device(self, x, order, t_T, t_0, h_init, atol, rtol, theta, t_err, solver_type):
+        """dpm_solver_adaptive with the controller on the device (csrc/adaptive_ctl.cu): s, lambda_s, h and the
+        accept/reject decision never visit the host; every fused launch reads its scalars from the coefficient
+        block the plan kernel wrote; `adaptive_chunk` iterations are enqueued per read of the `done` flag."""
+        be, ns = ops.backend(), self.noise_schedule
+        w = self._wrapped
+        discrete_in = isinstance(w, WrappedModel) and w.noise_schedule.schedule == 'discrete'
+        ctl = be.adaptive_controller(ns, x.device, order=order, predict_x0=self._pp, taylor=solver_type == 'taylor',
+                                     t_0=t_0, theta=theta, t_err=t_err, discrete_input=discrete_in)
+        ctl.init(t_T, h_init)
+        x = x.clone()                 # the committed state: overwritten in place by accepted steps
+        x_prev = x.clone()
+        rows = w.input_rows(x.shape[0]) if isinstance(w, WrappedModel) else x.shape[0]
+        C = P.Coeffs
+        if order == 2:     # DPM-Solver-12 (:985-988): coefficient blocks 0 (lower), 1 (x -> x_s1), 2 (higher)
+            sp_low = P.SinglestepPlan(1, [None], [C(FORM_LIN1, 0., 0., order=1, dev=ctl.block(0))])
+            sp_high = P.SinglestepPlan(2, [None, None], [C(FORM_LIN1, 0., 0., order=2, dev=ctl.block(1)),
+                                                         C(ops.FORM_DIFF2, 0., 0., w0=1.0, c0_on_old=True, order=2, dev=ctl.block(2))])
+        else:              # DPM-Solver-23 (:989-992): blocks 0 (x -> x_s1), 1 (lower), 2 (x -> x_s2), 3 (higher)
+            sp_low = P.SinglestepPlan(2, [None, None], [C(FORM_LIN1, 0., 0., order=2, dev=ctl.block(0)),
+                                                        C(ops.FORM_DIFF2, 0., 0., w0=1.0, c0_on_old=True, order=2, dev=ctl.block(1))])
+            fin = C(FORM_SS3T, 0., 0., order=3, dev=ctl.block(3)) if solver_type == 'taylor' else \
+                C(ops.FORM_DIFF2, 0., 0., w0=1.0, c0_on_old=True, order=3, dev=ctl.block(3))
+            sp_high = P.SinglestepPlan(3, [None, None, None], [C(FORM_LIN1, 0., 0., order=3, dev=ctl.block(0)),
+                                                               C(ops.FORM_DIFF2, 0., 0., w0=1.0, c0_on_old=True, order=3, dev=ctl.block(2)),
+                                                               fin])
+        n_high = len(sp_high.times)
+        td = [ctl.time(j) for j in range(n_high)]
+        tin = [ctl.input_time(j).expand(rows) for j in range(n_high)] if discrete_in else [None] * n_high
+        dev_als = [_DEV] * n_high
+        sharded = self.plan_broadcast and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        n_low = len(sp_low.times)
+        while True:
+            for _ in range(max(1, int(self.adaptive_chunk))):
+                ctl.plan()
+                x_lower, ms = self._run_singlestep(x, sp_low, keep=True, times_dev=td[:n_low], alsig=dev_als[:n_low],
+                                                   t_inputs=tin[:n_low])
+                x_higher, _ = self._run_singlestep(x, sp_high, model_s=ms[0], model_s1=ms[1] if order == 3 else None,
+                                                   times_dev=td, alsig=dev_als, t_inputs=tin)
+                be.error_norm(x_higher, x_lower, x_prev, atol, rtol, out=ctl.E)      # :999-1001, one fused reduction
+                if sharded:
+                    dist.all_reduce(ctl.E, op=dist.ReduceOp.MAX)                    # E is a max over the batch (:1001)
+                ctl.decide()                                                          # :1002-1008 on the device
+                ctl.select_copy(x, x_higher)
+                ctl.select_copy(x_prev, x_lower)
+            done, nfe, _ = ctl.read()                                                 # the chunk's only host sync
+            if done == 2:
+                raise FloatingPointError("dpm_solver_adaptive: the error estimate is NaN (the network output diverged)")
+            if done:
+                break
         print('adaptive solver nfe', nfe)
         return x
 

@@ -125,6 +125,11 @@ typedef struct dpm_step_desc {
   float sigma_e;
   float a, c0, c1, c2; /* update coefficients (signs folded in)                            */
   float w0, w1, w2, w3, w4;
+  /* Optional (NULL = off): the launch reads its scalars from DEVICE memory instead of the by-value fields above --
+   * 16 floats {a, c0, c1, c2, w0, w1, w2, w3, w4, alpha_e, sigma_e, 5 reserved}, written earlier on the same stream
+   * by dpm_adaptive_plan(): the on-device step-size controller of dpm_solver_adaptive (:956-1010), whose next
+   * coefficients depend on an accept/reject decision the host never sees. Served by the generic kernel. */
+  const float* dev_coef;
 } dpm_step_desc;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -245,6 +250,46 @@ DPM_API int dpm_adaptive_error(float* e_out, const void* x_higher, const void* x
                                const void* x_prev, float atol, float rtol, uint64_t per_sample,
                                uint64_t n, int dtype, void* workspace, size_t workspace_bytes,
                                dpm_stream_t stream);
+
+/* ---- dpm_solver_adaptive with the controller on the device (:956-1010) -------------------------------------
+ * Device buffers (caller-allocated, fp32): state[16] (s, lambda_s, lambda_0, h, t, nfe, done, accept, iterations as
+ * int bit patterns where integral), coef[4][16] (one dpm_step_desc.dev_coef block per fused launch of an
+ * iteration), times[6] (evaluation times s, s1, s2, then the model-input times the network receives), error[1]
+ * (written by dpm_adaptive_error). Schedule: discrete (tables as NoiseScheduleVP holds them, plus their flipped
+ * copies, all on the device) or the continuous linear VPSDE.
+ *   dpm_adaptive_init   : s = t_T, lambda_s, lambda_0, h = h_init                                      :972-977
+ *   dpm_adaptive_plan   : t = lambda^-1(lambda_s + h) and every coefficient block / time label of the
+ *                         lower- and higher-order updates of this iteration                             :984-992
+ *   dpm_adaptive_decide : E <= 1 ? accept (s = t, lambda_s) ; h = min(theta*h*E^(-1/order), lambda_0 - lambda_s);
+ *                         nfe += order; done = |s - t_0| <= t_err (2 = NaN error estimate)              :1002-1008
+ *   dpm_select_copy     : dst <- src iff the last decide accepted (x <- x_higher, x_prev <- x_lower)     :1003-1005
+ * Launch order per iteration for order 2: plan, [net(x,s)] step(coef 0: x_lower), step(coef 1: x_s1, pure),
+ * [net(x_s1,s1)] step(coef 2: x_higher), error, decide, select_copy x2; order 3 uses coef 0..3 (see
+ * dpm_solver_b200/solver.py). After `done` the plan emits identity coefficients, so a fixed-length chunk of
+ * iterations can be enqueued (or graph-captured) and `done` read back once per chunk. */
+typedef struct dpm_adaptive_ctl {
+  int32_t schedule_kind;       /* 0 discrete, 1 linear */
+  int32_t table_len;
+  const float* t_array;        /* device, [table_len] */
+  const float* log_alpha_array;
+  const float* log_alpha_flipped;
+  const float* t_flipped;
+  float beta_0, beta_1_minus_beta_0, inv_total_N;
+  int32_t discrete_time_input; /* 1: the network takes (t - 1/N)*1000 (:278), 0: t */
+  int32_t order;               /* 2 or 3 */
+  int32_t predict_x0;          /* dpmsolver++ */
+  int32_t taylor;              /* solver_type == 'taylor' */
+  float t_0, theta, t_err;
+  float* state;                /* device [16] */
+  float* coef;                 /* device [4][16] */
+  float* times;                /* device [6] */
+  const float* error;          /* device [1] */
+} dpm_adaptive_ctl;
+
+DPM_API int dpm_adaptive_init(const dpm_adaptive_ctl* ctl, float t_T, float h_init, dpm_stream_t stream);
+DPM_API int dpm_adaptive_plan(const dpm_adaptive_ctl* ctl, dpm_stream_t stream);
+DPM_API int dpm_adaptive_decide(const dpm_adaptive_ctl* ctl, dpm_stream_t stream);
+DPM_API int dpm_select_copy(void* dst, const void* src, const float* state, uint64_t bytes, dpm_stream_t stream);
 
 #ifdef __cplusplus
 }

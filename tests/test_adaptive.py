@@ -59,3 +59,86 @@ def test_error_norm_kernel(cuda_backend, shape, dt):
     delta = np.maximum(0.0078, 0.05 * np.maximum(np.abs(l), np.abs(p)))
     ref = np.sqrt(np.mean(np.square(((h - l) / delta).reshape(shape[0], -1)), axis=-1)).max()
     assert abs(got - ref) <= 2e-6 * ref
+
+
+# ---- the controller on the device (csrc/adaptive_ctl.cu) ------------------------------------------------------------
+def _adaptive_cfgs(n, seed):
+    import random
+    from test_random_configs_vs_reference import draw_wide
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        c = draw_wide(rng)
+        c.update(method="adaptive", order=rng.choice([2, 3]), atol=rng.choice([0.0078, 0.05]), rtol=rng.choice([0.05, 0.2]),
+                 thresholding=False, denoise_to_zero=False)
+        if c["schedule"] == "iddpm_cosine":
+            continue
+        out.append(c)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", range(4))
+def test_device_controller_matches_reference(cuda_backend, chunk):
+    """Random adaptive configurations (schedules, both algorithms and solver types, all parameterisations, CFG,
+    t_start / t_end, batch shapes): the device-side controller takes the accept/reject decisions of the UNMODIFIED
+    reference (same NFE) and lands on its sample within the reduction-order / device-libm tolerance."""
+    import contextlib
+    import io
+    import dpm_solver_b200 as new
+    from oracle import ref_loader
+    from test_random_configs_vs_reference import run_wide
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    ref = ref_loader.load("dpm_solver_pytorch")
+
+    class OnGpu:        # run_wide() builds CPU tensors: move the product arm to the device
+        NoiseScheduleVP = new.NoiseScheduleVP
+
+        @staticmethod
+        def model_wrapper(net, ns, **kw):
+            kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
+            return new.model_wrapper(net, ns, **kw)
+
+        class DPM_Solver(new.DPM_Solver):
+            def sample(self, x, **kw):
+                return super().sample(x.cuda(), **kw).cpu()
+
+    seen_device = 0
+    for c in _adaptive_cfgs(10, 9000 + chunk):
+        out_r, out_n = io.StringIO(), io.StringIO()
+        with contextlib.redirect_stdout(out_r):
+            yr, _, _ = run_wide(ref, c)
+        if not torch.isfinite(yr).all():
+            continue
+        before = cuda_backend.launch_count()
+        with contextlib.redirect_stdout(out_n):
+            yn, _, _ = run_wide(OnGpu, c)
+        seen_device += cuda_backend.launch_count() > before
+        assert out_n.getvalue().split()[-1] == out_r.getvalue().split()[-1], ("NFE", c)
+        assert rel_err(yn.numpy(), yr.numpy()) <= 5e-4, c
+    assert seen_device
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
+def test_device_controller_syncs_once_per_chunk(gold, cuda_backend, capsys, monkeypatch, c):
+    """The only device->host read of the adaptive loop is AdaptiveController.read(): once per `adaptive_chunk`
+    iterations. Same NFE and sample as the host controller (the reference's per-iteration decision)."""
+    from dpm_solver_b200 import DPM_Solver, model_wrapper, ops
+    reads = []
+    orig = ops.AdaptiveController.read
+
+    def counting(self):
+        r = orig(self)
+        reads.append(r)
+        return r
+    monkeypatch.setattr(ops.AdaptiveController, "read", counting)
+    y_dev, nfe_dev = run(c, "cuda:0", capsys)
+    iters = reads[-1][2]
+    assert len(reads) == -(-iters // DPM_Solver.adaptive_chunk) and reads[-1][0] == 1
+    assert nfe_dev == int(gold[c["name"] + "/nfe"]) == iters * c["order"]
+    monkeypatch.setattr(DPM_Solver, "adaptive_controller", "host")
+    y_host, nfe_host = run(c, "cuda:0", capsys)
+    assert nfe_host == nfe_dev
+    assert rel_err(y_dev.cpu().numpy(), y_host.cpu().numpy()) <= 1e-5

@@ -50,13 +50,16 @@ def test_argument_validation_needs_no_gpu():
 
 
 def test_struct_layout_matches_header():
-    """ctypes mirror of dpm_step_desc: 11 pointers, 2 u64, 8 i32, 12 floats."""
+    """ctypes mirror of dpm_step_desc: 11 pointers, 2 u64, 8 i32, 12 floats, 1 pointer; and of dpm_adaptive_ctl."""
     from dpm_solver_b200 import _lib
-    assert C.sizeof(_lib.StepDesc) == 11 * 8 + 2 * 8 + 8 * 4 + 12 * 4
+    assert C.sizeof(_lib.StepDesc) == 11 * 8 + 2 * 8 + 8 * 4 + 12 * 4 + 8
     src = open(os.path.join(ROOT, "include", "dpm_solver_b200.h")).read()
     body = src[src.index("typedef struct dpm_step_desc {"):src.index("} dpm_step_desc;")]
     names = re.findall(r"\b(\w+)\s*(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert [n for n, _ in _lib.StepDesc._fields_] == names
+    body = src[src.index("typedef struct dpm_adaptive_ctl {"):src.index("} dpm_adaptive_ctl;")]
+    names = re.findall(r"\b(\w+)\s*(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert [n for n, _ in _lib.AdaptiveCtl._fields_] == names
 
 
 def test_cpu_tensors_are_refused():
