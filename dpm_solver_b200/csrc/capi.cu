@@ -221,14 +221,14 @@ static int step_impl(const dpm_step_desc* d, cudaStream_t stream) {
   Tuning t{g_variant.load(), g_threads.load(), g_ctas.load()};
 
   bool body_done = false;
-  if (p.npk > 0 && all_aligned(p, nd) && p.raw_round == 0 && p.dev_coef == nullptr) {   // reference-rounding mode and
-                                                                                       // device-side scalars: generic kernel only
+  if (p.npk > 0 && all_aligned(p, nd) && p.dev_coef == nullptr) {   // device-side scalars: generic kernel only
     int r = 1;
     // small launches (a few tiles per SM) gain nothing from the ring; auto keeps them direct
     // fp32 state: direct 256-bit loads sit at the HBM roofline already (fewer instructions per
     // byte); 16-bit state is issue-limited there and gains 10-20% from the ring (profiles/)
-    const bool tma = t.variant == 1 || (t.variant == 2 && p.state_dtype != DPM_F32 &&
-                                         p.npk >= (uint32_t)sm_count() * 1024u);
+    const bool tma = p.raw_round == 0 &&   // reference-rounding mode: the direct variant's <RND> kernels
+                     (t.variant == 1 || (t.variant == 2 && p.state_dtype != DPM_F32 &&
+                                         p.npk >= (uint32_t)sm_count() * 1024u));
     if (tma) r = launch_step_tma(p, t, stream);
     if (r == 1) r = launch_step_direct(p, t, stream);
     if (r < 0 || r > 1) return r;

@@ -16,7 +16,10 @@ constexpr int kMaxThreads = 512;
 
 // FAST: the straight-line packet code of common.cuh (fast_model8 / fast_update8; launch-time test
 // fast_path_ok). FAST = false keeps every parameterisation, per-element thresholds and IEEE divisions.
-template <typename TE, typename TS, int NE, int FORM, bool FAST>
+// RND (only with FAST = false): reference-rounding mode (dpm_step_desc.raw_round) on the vector path -- the 16-bit
+// CFG combine (three rounded ops) and the rounded differences of raw 16-bit buffers, per element, between 128/256-bit
+// loads and stores.
+template <typename TE, typename TS, int NE, int FORM, bool FAST, bool RND = false>
 __global__ void __launch_bounds__(kMaxThreads)
     k_step_direct(const __grid_constant__ KParams p) {
   using Needs = FormNeeds<FORM>;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kMaxThreads)
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            fT[i] = model_value<NE>(p, fxe[i], fec[i], NE == 2 ? feu[i] : 0.f, thr8[i], clamp);
+            fT[i] = model_value<NE, RND>(p, fxe[i], fec[i], NE == 2 ? feu[i] : 0.f, thr8[i], clamp);
           Raw<TS> rmo;
           round_pack(rmo, fT);
           if (gmo != nullptr) stg_pk(gmo + e, rmo);
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(kMaxThreads)
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              fo[i] = update_value<FORM>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f,
-                                         Needs::kM2 ? fm2[i] : 0.f);
+              fo[i] = update_value<FORM, RND>(p, fx[i], fT[i], Needs::kM1 ? fm1[i] : 0.f,
+                                              Needs::kM2 ? fm2[i] : 0.f);
           }
           Raw<TS> ro;
           pack(ro, fo);
@@ -239,8 +242,32 @@ static StepKernel pick_direct(int md, int sd, int ne, int form, bool fast) {
   return nullptr;  // other mixes run on the generic kernel
 }
 
+// reference-rounding mode: fp32 state; raw network outputs in bf16 / f16 (NE >= 1), or fp32 buffers holding such raw
+// outputs (NE == 0, differences rounded)
+template <typename TE, int NE>
+static StepKernel pick_rnd_form(int form) {
+  switch (form) {
+    case DPM_FORM_NONE: return NE > 0 ? k_step_direct<TE, float, NE, DPM_FORM_NONE, false, true> : nullptr;
+    case DPM_FORM_LIN1: return k_step_direct<TE, float, NE, DPM_FORM_LIN1, false, true>;
+    case DPM_FORM_LIN2: return k_step_direct<TE, float, NE, DPM_FORM_LIN2, false, true>;
+    case DPM_FORM_LIN3: return k_step_direct<TE, float, NE, DPM_FORM_LIN3, false, true>;
+    case DPM_FORM_DIFF2: return k_step_direct<TE, float, NE, DPM_FORM_DIFF2, false, true>;
+    case DPM_FORM_MS3: return k_step_direct<TE, float, NE, DPM_FORM_MS3, false, true>;
+    case DPM_FORM_SS3T: return k_step_direct<TE, float, NE, DPM_FORM_SS3T, false, true>;
+  }
+  return nullptr;
+}
+static StepKernel pick_rnd(int md, int sd, int ne, int form) {
+  if (sd != DPM_F32) return nullptr;
+  if (ne == 0) return pick_rnd_form<float, 0>(form);
+  if (md == DPM_BF16) return ne == 1 ? pick_rnd_form<__nv_bfloat16, 1>(form) : pick_rnd_form<__nv_bfloat16, 2>(form);
+  if (md == DPM_F16) return ne == 1 ? pick_rnd_form<__half, 1>(form) : pick_rnd_form<__half, 2>(form);
+  return nullptr;
+}
+
 int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream) {
-  StepKernel k = pick_direct(p.model_dtype, p.state_dtype, p.n_model, p.form, fast_path_ok(p));
+  StepKernel k = p.raw_round ? pick_rnd(p.model_dtype, p.state_dtype, p.n_model, p.form)
+                             : pick_direct(p.model_dtype, p.state_dtype, p.n_model, p.form, fast_path_ok(p));
   if (k == nullptr) return 1;  // not served here
   const int threads = t.threads > 0 ? t.threads : 256;
   const uint32_t tile_pk = (uint32_t)threads * kUnroll;

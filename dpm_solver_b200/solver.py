@@ -510,20 +510,25 @@ class DPM_Solver:
         code = self._rr_code(raw)
         rr = 0
         if code:
-            if raw.e_uncond is not None:
-                # the reference's 16-bit CFG combine, materialised (values exactly representable in the
-                # network's type, held in fp32); everything downstream then sees a single noise tensor
+            # reference-rounding mode (raw 16-bit NOISE outputs, fp32 state): bits 0-1 make the fused kernel take the
+            # CFG combine in the network's type, three rounded ops (:329-330); for the eps-solver the buffered values
+            # are those raw outputs, so bit 2 makes their differences round too (:823, :880-881, :636, :735)
+            rr = code
+            if not x0:
+                rr = self._rr_run = code | 4
+            if raw.e_uncond is not None and x0 and self._dynamic_thresholding:
+                # the quantile kernels take the combine in fp32: give them (and the step) the reference's rounded
+                # noise, materialised once (values exactly representable in the network's type, held in fp32)
                 e = be.step(StepArgs(form=FORM_NONE, n_model=2, e_cond=raw.e_cond, e_uncond=raw.e_uncond,
                                      param=PARAM_NOISE, guidance=raw.guidance, state_dtype=torch.float32,
                                      raw_round=code))[0]
                 raw = RawOutput(e, None, PARAM_NOISE, 1.0)
-            if not x0:
-                rr = self._rr_run = code | 4       # eps-solver: the buffers are raw 16-bit outputs
-        if rr and co is not None:
+                rr = 0
+        if (rr & 4) and co is not None:
             co = self._rr_coeffs(co, code)
         if not self._needs_conversion(raw, sd, x0):
             m_new = raw.e_cond if ops.CudaBackend._layout(raw.e_cond) is not None else raw.e_cond.contiguous()
-            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr, pkey=pkey if m_new is raw.e_cond else None) \
+            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr & 4 and rr, pkey=pkey if m_new is raw.e_cond else None) \
                 if co is not None else None
             return m_new, x_next
         a = self._conv_args(raw, xe, alsig, sd, x0)
@@ -537,10 +542,11 @@ class DPM_Solver:
                                          float(self.thresholding_max_val))
         if custom_fix or co is None:
             a.form = FORM_NONE
+            a.raw_round = rr & 3
             m_new = be.step(a)[0]
             if custom_fix:
                 m_new = self._state_like(self.correcting_x0_fn(m_new, t_dev), sd)
-            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr) if co is not None else None
+            x_next = self._pure_update(co, x, m_new, m1, m2, rr=rr & 4 and rr) if co is not None else None
             return m_new, x_next
         self._fill_update(a, co, x, m1, m2)
         a.want_m_out = want_m
