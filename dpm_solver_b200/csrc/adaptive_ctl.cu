@@ -17,7 +17,8 @@
 // The host enqueues a fixed-length chunk of iterations and reads `done`/`nfe` back once per chunk. After `done`
 // the plan kernel emits identity coefficients at t_0, so the surplus iterations of a chunk leave x untouched.
 //
-// Schedule scalars use the device's expf/logf/expm1f/sqrtf, which differ from the host's in the last ulp: results
+// Schedule scalars use correctly rounded exp/log/expm1 (fp64, rounded once); the host's differ in the last ulp of
+// some arguments: results
 // agree with the reference to the north-star tolerance (like the reference itself run on CUDA vs CPU), the
 // accept/reject sequence -- hence NFE -- is identical unless E lands within ~1e-6 of 1 (tests/test_adaptive.py).
 #include <math.h>
@@ -54,6 +55,14 @@ struct AdaptCfg {
 
 enum { ST_S = 0, ST_LAM_S = 1, ST_LAM_0 = 2, ST_H = 3, ST_T = 4, ST_NFE = 5, ST_DONE = 6, ST_ACCEPT = 7, ST_ITERS = 8, ST_WORDS = 16 };
 
+// Transcendentals: evaluated in fp64 and rounded once, i.e. correctly rounded fp32 results. The host's (SLEEF) fp32
+// functions are within one ulp of that, and these formulas amplify an ulp (phi_3 = phi_2/h - 0.5 cancels), so the
+// closer the scalars the closer the adaptive path follows the reference's; one thread runs this, fp64 costs nothing.
+__device__ __forceinline__ float exp_cr(float v) { return (float)exp((double)v); }
+__device__ __forceinline__ float log_cr(float v) { return (float)log((double)v); }
+__device__ __forceinline__ float expm1_cr(float v) { return (float)expm1((double)v); }
+__device__ __forceinline__ float log1p_cr(float v) { return (float)log1p((double)v); }
+
 // y(x) on ascending keypoints, linear extrapolation, the reference's bracket rule (schedule.py _piecewise_linear)
 __device__ float interp(const float* xp, const float* yp, int K, float x) {
   int lo = 0, hi = K;                      // i = #{xp < x}
@@ -68,7 +77,7 @@ __device__ float interp(const float* xp, const float* yp, int K, float x) {
 }
 __device__ float logaddexp0(float v) {     // logaddexp(0, v) as ATen computes it: max + log1p(exp(-|a - b|))
   const float m = fmaxf(0.f, v);
-  return m + log1pf(expf(-fabsf(v)));
+  return m + log1p_cr(exp_cr(-fabsf(v)));
 }
 __device__ float log_alpha_of(const SchedDev& ns, float t) {
   if (ns.kind == 0) return interp(ns.t, ns.la, ns.K, t);                       // :129
@@ -88,10 +97,10 @@ __device__ Marg marg(const SchedDev& ns, float t) {
   Marg m;
   m.t = t;
   m.la = log_alpha_of(ns, t);
-  const float e2 = 1.f - expf(2.f * m.la);
+  const float e2 = 1.f - exp_cr(2.f * m.la);
   m.sigma = sqrtf(e2);                    // :146
-  m.lam = m.la - 0.5f * logf(e2);         // :153-154
-  m.alpha = expf(m.la);                   // :140
+  m.lam = m.la - 0.5f * log_cr(e2);         // :153-154
+  m.alpha = exp_cr(m.la);                   // :140
   return m;
 }
 
@@ -105,8 +114,8 @@ __device__ void put(float* b, float a, float c0, float c1, float c2, float w0, f
 // dpm_solver_first_update :563-588
 __device__ void first_update(bool pp, const Marg& ms, const Marg& mt, float& a, float& c0) {
   const float h = mt.lam - ms.lam;
-  if (pp) { a = mt.sigma / ms.sigma; c0 = -(mt.alpha * expm1f(-h)); }
-  else { a = expf(mt.la - ms.la); c0 = -(mt.sigma * expm1f(h)); }
+  if (pp) { a = mt.sigma / ms.sigma; c0 = -(mt.alpha * expm1_cr(-h)); }
+  else { a = exp_cr(mt.la - ms.la); c0 = -(mt.sigma * expm1_cr(h)); }
 }
 
 __global__ void k_adapt_plan(const AdaptCfg c) {
@@ -142,14 +151,14 @@ __global__ void k_adapt_plan(const AdaptCfg c) {
     tt[1] = s1;
     float a1, c01, af, bf, c1f;
     if (pp) {
-      a1 = m1.sigma / ms.sigma; c01 = -(m1.alpha * expm1f(-r1 * h));
-      const float phi_1 = expm1f(-h);
+      a1 = m1.sigma / ms.sigma; c01 = -(m1.alpha * expm1_cr(-r1 * h));
+      const float phi_1 = expm1_cr(-h);
       af = mt.sigma / ms.sigma; bf = mt.alpha * phi_1;
       c1f = c.taylor ? (1.f / r1) * (mt.alpha * (phi_1 / h + 1.f)) : -((0.5f / r1) * bf);
     } else {
-      a1 = expf(m1.la - ms.la); c01 = -(m1.sigma * expm1f(r1 * h));
-      const float phi_1 = expm1f(h);
-      af = expf(mt.la - ms.la); bf = mt.sigma * phi_1;
+      a1 = exp_cr(m1.la - ms.la); c01 = -(m1.sigma * expm1_cr(r1 * h));
+      const float phi_1 = expm1_cr(h);
+      af = exp_cr(mt.la - ms.la); bf = mt.sigma * phi_1;
       c1f = c.taylor ? -((1.f / r1) * (mt.sigma * (phi_1 / h - 1.f))) : -((0.5f / r1) * bf);
     }
     put(co + 1 * CO_WORDS, a1, c01, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, ms.alpha, ms.sigma);
@@ -162,8 +171,8 @@ __global__ void k_adapt_plan(const AdaptCfg c) {
     tt[1] = s1; tt[2] = s2;
     float a1, c01, at, bt, c1low, a2, c02, c12, c1fin, c2fin = 0.f, c1tay = 0.f;
     if (pp) {
-      const float phi_11 = expm1f(-r1 * h), phi_12 = expm1f(-r2 * h), phi_1 = expm1f(-h);
-      const float phi_22 = expm1f(-r2 * h) / (r2 * h) + 1.f, phi_2 = phi_1 / h + 1.f, phi_3 = phi_2 / h - 0.5f;
+      const float phi_11 = expm1_cr(-r1 * h), phi_12 = expm1_cr(-r2 * h), phi_1 = expm1_cr(-h);
+      const float phi_22 = expm1_cr(-r2 * h) / (r2 * h) + 1.f, phi_2 = phi_1 / h + 1.f, phi_3 = phi_2 / h - 0.5f;
       a1 = m1.sigma / ms.sigma; c01 = -(m1.alpha * phi_11);
       at = mt.sigma / ms.sigma; bt = mt.alpha * phi_1;
       c1low = c.taylor ? (1.f / r1) * (mt.alpha * (phi_1 / h + 1.f)) : -((0.5f / r1) * bt);
@@ -171,12 +180,12 @@ __global__ void k_adapt_plan(const AdaptCfg c) {
       c1fin = (1.f / r2) * (mt.alpha * phi_2);
       c1tay = mt.alpha * phi_2; c2fin = -(mt.alpha * phi_3);
     } else {
-      const float phi_11 = expm1f(r1 * h), phi_12 = expm1f(r2 * h), phi_1 = expm1f(h);
-      const float phi_22 = expm1f(r2 * h) / (r2 * h) - 1.f, phi_2 = phi_1 / h - 1.f, phi_3 = phi_2 / h - 0.5f;
-      a1 = expf(m1.la - ms.la); c01 = -(m1.sigma * phi_11);
-      at = expf(mt.la - ms.la); bt = mt.sigma * phi_1;
+      const float phi_11 = expm1_cr(r1 * h), phi_12 = expm1_cr(r2 * h), phi_1 = expm1_cr(h);
+      const float phi_22 = expm1_cr(r2 * h) / (r2 * h) - 1.f, phi_2 = phi_1 / h - 1.f, phi_3 = phi_2 / h - 0.5f;
+      a1 = exp_cr(m1.la - ms.la); c01 = -(m1.sigma * phi_11);
+      at = exp_cr(mt.la - ms.la); bt = mt.sigma * phi_1;
       c1low = c.taylor ? -((1.f / r1) * (mt.sigma * (phi_1 / h - 1.f))) : -((0.5f / r1) * bt);
-      a2 = expf(m2.la - ms.la); c02 = -(m2.sigma * phi_12); c12 = -(r2 / r1 * (m2.sigma * phi_22));
+      a2 = exp_cr(m2.la - ms.la); c02 = -(m2.sigma * phi_12); c12 = -(r2 / r1 * (m2.sigma * phi_22));
       c1fin = -((1.f / r2) * (mt.sigma * phi_2));
       c1tay = -(mt.sigma * phi_2); c2fin = -(mt.sigma * phi_3);
     }

@@ -180,7 +180,7 @@ def test_plan_kernel_coefficients_match_host_plan(cuda_backend, schedule, algo, 
 
         def close(block, co, alsig_time):
             want = [co.a, co.c0, co.c1, co.c2]
-            np.testing.assert_allclose(block[:4], want, rtol=3e-5, atol=2e-6)
+            np.testing.assert_allclose(block[:4], want, rtol=3e-5, atol=5e-6)   # phi_3 = phi_2/h - 0.5 cancels: an ulp of expm1f is 3e-4 of it
             if co.form == 6:
                 np.testing.assert_allclose(block[4:9], [co.w0, co.w1, co.w2, co.w3, co.w4], rtol=1e-6)
             al, sg = float(ns.marginal_alpha(alsig_time)), float(ns.marginal_std(alsig_time))

@@ -39,6 +39,8 @@ l2ncu)
   timeout 400 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct -k regex:k_step_direct --csv --log-file gpurun_out/l2_ncu.csv python tools/l2_group_probe.py 16 24 32 48 64 > gpurun_out/l2_ncu.log 2>&1; python tools/l2_ncu_digest.py gpurun_out/l2_ncu.csv ;;
 l2probe)
   timeout 300 python tools/l2_group_probe.py > gpurun_out/l2_group_probe.txt 2>&1; cat gpurun_out/l2_group_probe.txt ;;
+adaptive_probe)
+  timeout 600 python tools/adaptive_probe.py > gpurun_out/adaptive_probe.txt 2>&1; cat gpurun_out/adaptive_probe.txt ;;
 latency)
   timeout 600 python tools/host_overhead.py > gpurun_out/host_overhead.txt 2>&1; cat gpurun_out/host_overhead.txt ;;
 *) echo "unknown stage $stage" ;;

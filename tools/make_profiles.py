@@ -54,8 +54,9 @@ def main():
           "All numbers measured on one B200 (sm_100a) of this pool through `gpurun`; HBM peak denominator = "
           "`MEASURED_PEAKS.json` `hbm_gbs` = 6574.5 GB/s (torch copy, read+write). Event timings come from "
           "`bench.py` (CUDA events on the launching stream, inputs > L2, >= 3 warm-ups); ncu timings are "
-          "cold-cache and serialised — compare shares, not absolutes. Regenerate with `bash tools/gpu_round.sh` "
-          "under gpurun, then `python tools/make_profiles.py`.", ""]
+          "cold-cache and serialised — compare shares, not absolutes. Regenerate with "
+          "`bash tools/gpu_run.sh tests_all smoke bench bench_each ref launches ncu_step ncu_quantile latency` under gpurun, "
+          f"then `python tools/make_profiles.py --round {R}`. Earlier rounds: `profiles/r01_README.md`.", ""]
     traffic = {}
     # ---- bench lines ----
     md += ["## bench.py lines", "", "| workload | GElem/s | ms/step | HBM GB/s (all launches) | dominant kernel | achieved GB/s | frac of peak | e2e GElem/s | launches | SM MHz |", "|---|---|---|---|---|---|---|---|---|---|"]
@@ -79,8 +80,10 @@ def main():
         if lines:
             d = json.loads(lines[-1])
             json.dump(d, open(os.path.join(DST, f"{R}_bench_reference_arm.json"), "w"), indent=1)
-            md += ["", f"Reference arm (`bench.py --impl reference`, oracle port in its torch-CPU namespace): **{d['value']:.3f} GElem/s** on "
-                   f"{d['cpu_baseline']['cores']} host threads, sample {d['cpu_baseline']['sample']}."]
+            cb = d["cpu_baseline"]
+            what = "the UNMODIFIED reference from oracle/_ref on CPU tensors" if cb.get("kind") == "reference" else "oracle port in its torch-CPU namespace"
+            md += ["", f"Reference arm (`bench.py --impl reference`, {what}): **{d['value']:.3f} GElem/s** on "
+                   f"{cb['cores']} host threads (host has {cb.get('host_cores')} cores, {cb.get('usable_cores')} usable by the job), sample {cb['sample']}."]
     if "c2" in benches and "kernels_alone" in benches["c2"]:
         md += ["", "North-star kernel timed alone (fused 3rd-order multistep update, x + 3 buffers -> x_t, `[4096,4,64,64]`, rotating through 3 buffer sets):", "",
                "| kernel | bytes/launch | median µs | GB/s | frac of measured peak | GElem/s |", "|---|---|---|---|---|---|"]
@@ -88,12 +91,26 @@ def main():
             md.append(f"| {k} | {v['bytes_per_launch']} | {v['median_us']:.1f} | {v['gbs']:.0f} | {v['frac_of_peak']:.3f} | {v['gelem_s']:.0f} |")
         cb = benches["c2"].get("cpu_baseline")
         if cb:
-            md += ["", f"CPU baseline beside it (same job, rank 0): {cb['value']:.3f} GElem/s, {cb['cores']} threads, {cb['sample']}."]
+            md += ["", f"CPU baseline beside it (same job, rank 0, kind `{cb.get('kind')}`): {cb['value']:.3f} GElem/s, {cb['cores']} threads "
+                   f"of {cb.get('host_cores')} host cores, {cb['sample']}."]
         eg = benches["c2"].get("eager_cuda_baseline")
         if eg and "value" in eg:
-            md += ["", f"Second baseline, same GPU: the reference algorithm as stock eager PyTorch CUDA kernels (oracle port, torch namespace on "
-                   f"cuda, fp32 state, full C2 shape): **{eg['value']:.1f} GElem/s** ({eg['ms_per_step']:.1f} ms per 20-step sample()) — "
+            md += ["", f"Second baseline, same GPU: the reference (kind `{eg.get('kind')}`: `reference` = the unmodified file from oracle/_ref) as stock "
+                   f"eager PyTorch CUDA kernels, fp32 state, full C2 shape: **{eg['value']:.1f} GElem/s** ({eg['ms_per_step']:.1f} ms per 20-step sample()) — "
                    f"{benches['c2']['value'] / eg['value']:.0f}x below the fused bf16 path ({benches['c2']['value']:.0f} GElem/s)."]
+    for w, d in benches.items():
+        par = d.get("parity") or {}
+        md += ["", f"{w} parity (outside the timed region, {par.get('rows')} rows of the run's own output vs {par.get('reference')}): "
+               f"checked={par.get('parity_checked')}, max rel err {par.get('max_rel_err')}, rms rel err {par.get('rms_rel_err')}, "
+               f"bit_exact={par.get('bit_exact')}, bound={par.get('bound')}."]
+    if "c2" in benches and "workloads" in benches["c2"]:
+        md += ["", "The default `python bench.py` line (what the driver records) also carries the other single-GPU configs under `workloads`:", "",
+               "| workload | GElem/s | ms/step | dominant kernel | GB/s | frac | parity_checked |", "|---|---|---|---|---|---|---|"]
+        for n, o in benches["c2"]["workloads"].items():
+            if "error" in o:
+                md.append(f"| {n} | error: {o['error']} | | | | | |")
+            else:
+                md.append(f"| {n} | {o['value']:.1f} | {o['ms_per_step']:.3f} | `{o['roofline']['kernel']}` | {o['roofline']['achieved']:.0f} | {o['roofline']['frac']:.3f} | {o['config'].get('parity_checked')} |")
     md.append("")
     # ---- per-kernel event table + ncu launch share ----
     for w, d in benches.items():
@@ -118,12 +135,14 @@ def main():
             traffic[w][d["roofline"]["kernel"]] = (dom[2] + dom[3]) / dom[0]
             traffic[w]["_ncu_kernel"] = dom_k
         md.append("")
-    json.dump(traffic, open(os.path.join(DST, "roofline_traffic.json"), "w"), indent=1)
+    if traffic:
+        traffic["_source"] = f"profiles/{R}_launches_<workload>.csv"
+        json.dump(traffic, open(os.path.join(DST, "roofline_traffic.json"), "w"), indent=1)
     # ---- ncu full ----
     reps = sorted(f for f in os.listdir(SRC) if f.endswith(".ncu-rep"))
     pre = os.path.join(SRC, "ncu_summary.md")
     if os.path.exists(pre) and os.path.exists(os.path.join(SRC, "ncu_summary.json")):
-        # tools/gpu_round_final.sh summarised the captures on the GPU box (the .ncu-rep files stay there)
+        # tools/gpu_run.sh summarised the captures on the GPU box (the .ncu-rep files stay there)
         # merge by capture name: a partial round (e.g. only the quantile kernels re-captured) keeps the rest
         dmd, djs = os.path.join(DST, f"{R}_ncu_summary.md"), os.path.join(DST, f"{R}_ncu_summary.json")
         rows = OrderedDict()
@@ -166,7 +185,7 @@ def main():
             f = lambda r: f"{r['gbs']:.0f} ({r['threads']}×{r['ctas']})" if r else "-"
             md.append(f"| {k[0]} | {k[1]} | {k[2]} | {f(bd)} | {f(bt)} | {t22[0]['gbs']:.0f} |" if t22 else f"| {k[0]} | {k[1]} | {k[2]} | {f(bd)} | {f(bt)} | - |")
         md.append("")
-    for extra in ("host_overhead.txt",):
+    for extra in ("host_overhead.txt", "inloop_sweep.txt", "l2_group_probe.txt"):
         p = os.path.join(SRC, extra)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(DST, f"{R}_{extra}"))
