@@ -43,10 +43,11 @@ def test_adaptive_host_logic(gold, oracle_backend, capsys, c):
 @pytest.mark.gpu
 @pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
 def test_adaptive_gpu(gold, cuda_backend, capsys, monkeypatch, c):
-    """Default (device controller): the step sizes come from the device's expf/logf/expm1f, an ulp away from the
-    host's, and an adaptive solve amplifies that through h = theta*h*E^(-1/order): same decisions and NFE, the
-    sample within 1e-4 (order 3: 2.5e-5 .. 4.4e-5 measured; the reference itself differs as much between its CPU
-    and CUDA runs). Host controller (identical scalars): the north-star 1e-5."""
+    """Default (device controller): its scalars are correctly rounded fp32 (fp64 evaluation, one rounding), the host's
+    SLEEF results differ from that in the last ulp of a few arguments, and an adaptive solve amplifies an ulp through
+    h = theta*h*E^(-1/order): same decisions and NFE, the sample within 1e-4 -- on 40 random configurations it is
+    bit-identical to the reference's CPU run in 30 and within 5e-5 in the rest, while the reference's own CUDA run
+    strays up to 3e-2 and changes NFE once (profiles/r02_adaptive_probe.txt). Host controller: the north-star 1e-5."""
     from dpm_solver_b200 import DPM_Solver
     y, nfe = run(c, "cuda:0", capsys)
     assert nfe == int(gold[c["name"] + "/nfe"])
@@ -126,7 +127,7 @@ def test_device_controller_matches_reference(cuda_backend, chunk):
             yn, _, _ = run_wide(OnGpu, c)
         seen_device += cuda_backend.launch_count() > before
         assert pn.call_args[0][-1] == nfe_r, ("NFE", c)
-        assert rel_err(yn.numpy(), yr.numpy()) <= 5e-4, c
+        assert rel_err(yn.numpy(), yr.numpy()) <= 2e-4, c      # measured: 0 .. 5e-5 (profiles/r02_adaptive_probe.txt)
     assert seen_device
 
 
