@@ -543,7 +543,7 @@ class Ctx:
         return float(t.item())
 
 
-def build_solver(ctx, w, B, seed, inputs=None):
+def build_solver(ctx, w, B, seed, inputs=None, plan_broadcast=None):
     """Synthetic inputs (or the given (x_T, banks)) + the product solver for a B-sample batch of workload `w` on
     this rank's GPU."""
     from cases import make_betas
@@ -567,7 +567,7 @@ def build_solver(ctx, w, B, seed, inputs=None):
         fn = model_wrapper(net, ns)
     solver = DPM_Solver(fn, ns, algorithm_type=w["algo"], state_dtype=dt,
                         correcting_x0_fn="dynamic_thresholding" if w["thresholding"] else None,
-                        plan_broadcast=ctx.world > 1)
+                        plan_broadcast=(ctx.world > 1) if plan_broadcast is None else plan_broadcast)
     kw = dict(steps=w["steps"], order=w["order"], method=w["method"], skip_type="time_uniform")
     return solver, kw, x_T, banks, cnt
 
@@ -625,7 +625,8 @@ def shard_parity(ctx, w):
     dist.all_gather(gathered, y_s)
     ok = True
     if ctx.rank == 0:
-        solver_g, _, _, _, _ = build_solver(ctx, w, Bg, 0, inputs=(x_g, banks_g))
+        # rank 0 alone: no collective may be issued here (its own plan IS the one the shards were synced to)
+        solver_g, _, _, _, _ = build_solver(ctx, w, Bg, 0, inputs=(x_g, banks_g), plan_broadcast=False)
         ok = bool(torch.equal(torch.cat(gathered), solver_g.sample(x_g, **kw)))
     flag = torch.tensor([1 if ok else 0], device=ctx.dev)
     dist.broadcast(flag, 0)
