@@ -5,6 +5,7 @@
 #include <utility>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "launch.cuh"
@@ -22,6 +23,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DPM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 int sm_count() {
   static int cache[64] = {0};

@@ -21,6 +21,32 @@ void count_launch();                // bump the library launch counter
 int ensure_max_smem(const void* kernel, bool nonportable_cluster = false);
 void set_error(const char* fmt, ...);
 
+// Programmatic dependent launch (PDL): the step kernels call pdl_wait() after their prologue (barrier init, index
+// setup) and before touching global memory, and pdl_trigger() at entry; launched with the programmatic-stream-
+// serialization attribute, the CTAs of step i+1 become resident while step i drains and only their first global
+// access waits for its completion (and visibility). Without the attribute both are no-ops. Persistent one-wave grids
+// only, so an early dependent can never starve its primary.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // DPM_PDL=0 turns the launch attribute off (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // each returns 0 on launch, 1 if this variant does not serve the request, <0 / cudaError on error
 int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream);
 int launch_step_scalar(const KParams& p, cudaStream_t stream);

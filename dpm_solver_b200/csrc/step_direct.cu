@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kMaxThreads)
   const uint32_t tile_pk = blockDim.x * kUnroll;
   const bool sep_xe = (NE > 0) && p.use_xe && !(Needs::kX && p.xe_is_x);
   const bool clamp = (NE > 0) && (p.thr != nullptr);
+  pdl_trigger();
+  pdl_wait();
 
   for (uint64_t tile0 = (uint64_t)blockIdx.x * tile_pk; tile0 < npk;
        tile0 += (uint64_t)gridDim.x * tile_pk) {
@@ -275,7 +277,8 @@ int launch_step_direct(const KParams& p, const Tuning& t, cudaStream_t stream) {
   uint64_t cap = (uint64_t)sm_count() * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 8);
   uint32_t grid = (uint32_t)(tiles < cap ? tiles : cap);
   if (grid == 0) return 0;
-  k<<<grid, threads, 0, stream>>>(p);
+  cudaError_t le = launch_pdl(k, grid, (unsigned)threads, 0, stream, p);
+  if (le != cudaSuccess) { set_error("step launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return (int)le; }
   count_launch();
   return 0;
 }

@@ -149,11 +149,13 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   const char* gstate = static_cast<const char*>(Needs::kX ? p.x : p.xe);
   constexpr uint32_t kBS = Traits<TS>::kBytes * kPacket, kBM = Traits<TE>::kBytes * kPacket;   // bytes per packet
 
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(reinterpret_cast<uint64_t*>(smem) + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();   // everything above overlapped the previous launch's tail; global memory from here on
 
   auto issue_loads = [&](uint32_t tile, uint32_t s) {
     const uint32_t pk0 = tile * tile_pk;
@@ -364,7 +366,8 @@ int launch_step_tma(const KParams& p, const Tuning& t, cudaStream_t stream) {
   if (grid == 0) return 0;
   int rc = ensure_max_smem(reinterpret_cast<const void*>(k));  // once per kernel and device
   if (rc != 0) return rc;
-  k<<<grid, threads, smem, stream>>>(p, L, stages, units);
+  cudaError_t le = launch_pdl(k, grid, (unsigned)threads, smem, stream, p, L, stages, units);
+  if (le != cudaSuccess) { set_error("TMA step launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return (int)le; }
   count_launch();
   return 0;
 }

@@ -15,8 +15,8 @@ tests_all)
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log ;;
 bench)
-  timeout 900 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -c 600 gpurun_out/bench_c2.err
-  python tools/bench_digest.py gpurun_out/bench_c2.json ;;
+  timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.err
+  python tools/bench_digest.py gpurun_out/bench_default.json ;;
 bench_each)
   for w in c2 c3 c4; do timeout 600 python bench.py --workload $w --steps 5 --no-extras > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; python tools/bench_digest.py gpurun_out/bench_$w.json; done ;;
 ref)

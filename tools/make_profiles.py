@@ -63,6 +63,8 @@ def main():
     benches = {}
     for w in ("c2", "c3", "c4"):
         p = os.path.join(SRC, f"bench_{w}.json")
+        if w == "c2" and os.path.exists(os.path.join(SRC, "bench_default.json")):
+            p = os.path.join(SRC, "bench_default.json")       # the driver's command: carries workloads / kernels_alone / baselines
         if not os.path.exists(p):
             continue
         lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
