@@ -16,7 +16,7 @@ for path in sys.argv[1:]:
     def line(tag, o):
         r = o["roofline"]
         par = o.get("parity") or {}
-        print(f"{tag}: {o['value']:.1f} GElem/s  {o['ms_per_step']:.3f} ms/step  dom={r['kernel']} {r['achieved']:.0f} GB/s frac={r['frac']:.3f} "
+        print(f"{tag}: {o['value']:.1f} GElem/s  {o['ms_per_step']:.3f} ms/step (instrumented {o.get('ms_per_step_instrumented', 0):.3f})  dom={r['kernel']} {r['achieved']:.0f} GB/s frac={r['frac']:.3f} "
               f"total={o['hbm_gbs_total']:.0f} GB/s  parity={par.get('parity_checked')} max_rel={par.get('max_rel_err')}  clocks={o['clocks']}")
         for k, v in sorted(o["kernels"].items(), key=lambda kv: -kv[1]["ms"]):
             print(f"    {k:44s} n={v['launches']:4d} avg={v['avg_us']:8.1f} us  {v['gbs']:.0f} GB/s")
