@@ -1,8 +1,8 @@
 # Convenience targets (the driver uses __graft_entry__.build(), pytest and bench.py directly).
 PY ?= python
-.PHONY: build test test-gpu bench bench-ref profiles clean
+.PHONY: build test test-gpu bench bench-ref golden profiles clean
 build:
-	$(PY) -m dpm_solver_b200.build
+	$(PY) -c "import __graft_entry__ as g; g.build()"
 test: build
 	$(PY) -m pytest tests -q -m "not gpu"
 test-gpu: build
@@ -14,6 +14,6 @@ bench-ref:
 golden:
 	$(PY) tests/golden/make_golden.py
 profiles:
-	$(PY) tools/make_profiles.py --round r01
+	$(PY) tools/make_profiles.py --round r02
 clean:
-	rm -rf dpm_solver_b200/build dpm_solver_b200/lib
+	rm -rf dpm_solver_b200/build dpm_solver_b200/lib oracle/_ref

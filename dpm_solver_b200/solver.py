@@ -873,6 +873,9 @@ class DPM_Solver:
         ctl.init(t_T, h_init)
         x = x.clone()                 # the committed state: overwritten in place by accepted steps
         x_prev = x.clone()
+        # (a 16-bit x_T reaches the network widened to fp32 here -- same values; the by-identity hand-over of the
+        # caller's own tensor at the first evaluation, `_net_input`, cannot follow a buffer that is updated in place)
+        self._net_input = None
         rows = w.input_rows(x.shape[0]) if isinstance(w, WrappedModel) else x.shape[0]
         C = P.Coeffs
         if order == 2:     # DPM-Solver-12 (:985-988): coefficient blocks 0 (lower), 1 (x -> x_s1), 2 (higher)

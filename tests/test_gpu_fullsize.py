@@ -101,3 +101,34 @@ def test_non_default_stream_and_empty(cuda_backend):
     assert torch.equal(y, 0.5 * x + 0.25 * m)
     e = torch.empty(0, device=DEV)
     assert ops.lincomb(e, [e], 1.0, [1.0]).numel() == 0
+
+
+def test_beyond_2_31_elements(cuda_backend):
+    """Maximum sizes: more than 2^31 elements in one call (64-bit byte offsets, 32-bit packet indices) on both kernel
+    variants and the duplicate kernel -- bf16 keeps it at 4.3 GB per tensor. Checked on slices at the start, across
+    the 2^31 boundary and at the ragged tail against the unfused fp32 expression rounded to bf16."""
+    n = (1 << 31) + 8 * 1000 + 3
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(n, device=DEV, generator=g).bfloat16()
+    m0 = torch.randn(n, device=DEV, generator=g).bfloat16()
+    a, c0 = 0.9375, -0.40625
+    spots = [slice(0, 4096), slice((1 << 31) - 2048, (1 << 31) + 2048), slice(n - 3000, n)]
+
+    def want(sl):
+        return (a * x[sl].float() + c0 * m0[sl].float()).bfloat16()
+
+    for variant in (1, 0):
+        cuda_backend.set_tuning(variant=variant)
+        try:
+            out = ops.lincomb(x, [m0], a, [c0])
+        finally:
+            cuda_backend.set_tuning(variant=2)
+        for sl in spots:
+            assert torch.equal(out[sl], want(sl)), (variant, sl)
+        del out
+    del m0
+    xx = x.view(1, n)
+    dup = cuda_backend.duplicate(xx)
+    assert dup.shape == (2, n)
+    for sl in spots:
+        assert torch.equal(dup[0, sl], x[sl]) and torch.equal(dup[1, sl], x[sl])
