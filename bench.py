@@ -412,6 +412,16 @@ def make_timed_backend():
 
             return TimedPrepared()
 
+        def duplicate(self, x):
+            if not self.recording:
+                return super().duplicate(x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = super().duplicate(x)
+            e1.record()
+            self.records.append(("cat([x]*2)", 3 * x.numel() * x.element_size(), e0, e1))
+            return out
+
         def dynamic_threshold(self, a, q, max_val):
             if not self.recording:
                 return super().dynamic_threshold(a, q, max_val)

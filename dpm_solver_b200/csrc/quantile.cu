@@ -229,12 +229,14 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
   const uint64_t sample = blockIdx.x / cps;
   const uint32_t part = blockIdx.x % cps;
   uint32_t* hdr = qp.work + sample * H_WORDS;
-  const uint32_t lo_k = hdr[H_LO], hi_k = hdr[H_HI];
-  const float A_lo = __uint_as_float(hdr[H_ALO]), A_hi = __uint_as_float(hdr[H_AHI]);
   const bool num_space = qp.num_space != 0;
   const int tid = threadIdx.x;
   if (tid == 0) { s_n = 0; s_lt = 0; }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();      // the pivots kernel's header words (programmatic dependent launch: launch.cuh)
+  const uint32_t lo_k = hdr[H_LO], hi_k = hdr[H_HI];
+  const float A_lo = __uint_as_float(hdr[H_ALO]), A_hi = __uint_as_float(hdr[H_AHI]);
 
   uint32_t c_lt = 0, kmax = 0;   // kmax: largest |.| bit pattern seen (NaN detection, one integer max per element)
   // numerator space: 8 elements, ~8 instructions each and NO division at all: |num| -> |num / alpha| is
@@ -375,6 +377,8 @@ __global__ void __launch_bounds__(kPThreads) k_q_finish(const __grid_constant__ 
   const uint64_t sample = blockIdx.x;
   const int tid = threadIdx.x;
   uint32_t* hdr = qp.work + sample * H_WORDS;
+  pdl_trigger();
+  pdl_wait();      // the count kernel's counters and candidates
   const uint64_t C_lt = hdr[H_LT], C_in = hdr[H_IN];
   const bool bracket_ok = C_in <= qp.cap && qp.lo >= C_lt && (qp.lo + qp.two) < C_lt + C_in;
   if (tid == 0) {
@@ -698,7 +702,8 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     QKernel kp = p.n_model == 2 ? k_q_pivots<2> : k_q_pivots<1>;
     QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
     kp<<<(unsigned)n_samples, kPThreads, 0, stream>>>(p, qp);
-    kn<<<(unsigned)(n_samples * qp.slice), kPThreads, 0, stream>>>(p, qp);
+    e = launch_pdl(kn, (unsigned)(n_samples * qp.slice), kPThreads, 0, stream, p, qp);
+    if (e != cudaSuccess) { set_error("quantile count launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     // finish: stage the candidates in shared memory when they fit next to 3 co-resident CTAs (else read L2)
     QParams qf = qp;
     const size_t fsmem = (size_t)qp.cap * sizeof(uint32_t);
@@ -707,7 +712,8 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
       int rc = ensure_max_smem(reinterpret_cast<const void*>(kf));
       if (rc != 0) return rc;
     }
-    kf<<<(unsigned)n_samples, kPThreads, qf.slice ? fsmem : 0, stream>>>(p, qf);
+    e = launch_pdl(kf, (unsigned)n_samples, kPThreads, qf.slice ? fsmem : 0, stream, p, qf);
+    if (e != cudaSuccess) { set_error("quantile finish launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     count_launch();
     count_launch();
     count_launch();
