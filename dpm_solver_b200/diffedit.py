@@ -55,10 +55,5 @@ class DiffEditCorrector:
         x0 = self.init_latent
         if x0.dtype != x.dtype:
             x0 = x0.to(x.dtype)
-        if hasattr(be, "diffedit_corrector") and x.is_cuda:
-            return be.diffedit_corrector(x, x0.expand(x.shape) if x0.shape != x.shape else x0, self.mask.to(x.device),
-                                         alpha, sigma, self.generator)
-        # executors without in-kernel noise (the numpy executor of the CPU tests): the reference's op chain
-        noise = torch.randn((1, *x0.shape), device=x0.device, generator=self.generator)
-        inter = ops.lincomb(x0.contiguous(), [noise[0].to(x0.dtype)], alpha, [sigma])
-        return x * self.mask.to(x.device) + (1 - self.mask.to(x.device)) * inter
+        return be.diffedit_corrector(x, x0.expand(x.shape) if x0.shape != x.shape else x0, self.mask.to(x.device),
+                                     alpha, sigma, self.generator)

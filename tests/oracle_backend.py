@@ -142,6 +142,16 @@ class OracleBackend:
                 a.out2.copy_(out.reshape(a.out2.shape))
         return m_out, out
 
+    def diffedit_corrector(self, x, x0, mask, alpha, sigma, generator=None):
+        """x*mask + (1 - mask)*(alpha*x0 + sigma*randn_like(x0)) in numpy fp32, the noise from torch's CPU generator
+        exactly as `stochastic_encode` draws it (sampler.py:92-96 -> add_noise :1023-1024)."""
+        self.launches += 1
+        noise = torch.randn((1, *x0.shape), generator=generator)[0].numpy()
+        xf, x0f, m = _np(x), _np(x0), _np(mask)
+        inter = f32(alpha) * x0f + f32(sigma) * noise
+        out = xf * m + (f32(1) - m) * inter
+        return torch.from_numpy(np.ascontiguousarray(out.astype(f32))).to(x.dtype)
+
     def duplicate(self, x):
         self.launches += 1
         return torch.cat([x] * 2)
