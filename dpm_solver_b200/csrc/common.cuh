@@ -84,6 +84,25 @@ __device__ __forceinline__ void ldg_pk(Raw<T16>& v, const T16* p) {
                : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3])
                : "l"(p));
 }
+// the same loads with an L2 eviction-priority hint (createpolicy ... L2::evict_last / evict_first): used by experiments
+// on keeping a sample group's (x, eps) resident between the quantile's count pass and the step that re-reads them
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ldg_pk_hint(Raw<float>& v, const float* p, uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]),
+                 "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "l"(p), "l"(pol));
+}
+template <typename T16>
+__device__ __forceinline__ void ldg_pk_hint(Raw<T16>& v, const T16* p, uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3])
+               : "l"(p), "l"(pol));
+}
 __device__ __forceinline__ void stg_pk(float* p, const Raw<float>& v) {
   asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
                "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]),

@@ -51,6 +51,7 @@ struct QParams {
   uint64_t n_samples;
   uint32_t iters;     // count kernel: consecutive chunks per CTA
   uint32_t num_space; // pipeline: bracket keys are |numerator| patterns (plain eps -> x0 map, alpha > 0)
+  uint32_t evict_last; // experiment (DPM_Q_EVICT_LAST=1): count-pass loads ask L2 to keep the lines (evict_last)
 };
 // header words per sample
 enum { H_LO = 0, H_HI = 1, H_LT = 2, H_IN = 3, H_PATH = 4, H_ALO = 5, H_AHI = 6, H_NAN = 7, H_WORDS = 8 };
@@ -315,9 +316,16 @@ __global__ void __launch_bounds__(kPThreads) k_q_count(const __grid_constant__ K
         const uint32_t pk = u * kPThreads + tid;
         if (pk < npk) {
           const size_t e = e0 + (size_t)pk * kPacket;
-          ldg_pk(rx[u], gxe + e);
-          ldg_pk(rc[u], gec + e);
-          if (NE == 2) ldg_pk(ru[u], geu + e);
+          if (qp.evict_last) {
+            const uint64_t pol = l2_policy_evict_last();
+            ldg_pk_hint(rx[u], gxe + e, pol);
+            ldg_pk_hint(rc[u], gec + e, pol);
+            if (NE == 2) ldg_pk_hint(ru[u], geu + e, pol);
+          } else {
+            ldg_pk(rx[u], gxe + e);
+            ldg_pk(rc[u], gec + e);
+            if (NE == 2) ldg_pk(ru[u], geu + e);
+          }
         }
       }
 #pragma unroll
@@ -698,6 +706,7 @@ int launch_quantile(float* s_out, const KParams& p, uint64_t n_samples, float q,
     qp.work = static_cast<uint32_t*>(workspace);
     // division-free classification and |numerator| candidates need the plain eps -> x0 map with a positive alpha
     qp.num_space = (vec && p.param == DPM_PARAM_NOISE && p.predict_x0 && p.alpha_e > 0.f) ? 1u : 0u;
+    qp.evict_last = env_int("DPM_Q_EVICT_LAST", 0) ? 1u : 0u;
     if (n_samples * qp.slice > 0x7fffffffull) { set_error("too many chunks"); return DPM_ERR_UNSUPPORTED; }
     QKernel kp = p.n_model == 2 ? k_q_pivots<2> : k_q_pivots<1>;
     QKernel kf = p.n_model == 2 ? k_q_finish<2> : k_q_finish<1>;
