@@ -41,6 +41,8 @@ l2probe)
   timeout 300 python tools/l2_group_probe.py > gpurun_out/l2_group_probe.txt 2>&1; cat gpurun_out/l2_group_probe.txt ;;
 adaptive_probe)
   timeout 600 python tools/adaptive_probe.py > gpurun_out/adaptive_probe.txt 2>&1; cat gpurun_out/adaptive_probe.txt ;;
+sanitize)
+  for t in memcheck racecheck synccheck; do timeout 900 compute-sanitizer --tool $t python tools/sanitize_probe.py > gpurun_out/sanitizer_$t.log 2>&1; echo "$t rc=$?" >> gpurun_out/sanitizer_$t.log; tail -3 gpurun_out/sanitizer_$t.log; done ;;
 latency)
   timeout 600 python tools/host_overhead.py > gpurun_out/host_overhead.txt 2>&1; cat gpurun_out/host_overhead.txt ;;
 *) echo "unknown stage $stage" ;;

@@ -44,5 +44,24 @@ for per_sample, B in ((24, 7), (4 * 64 * 64, 5), (3 * 128 * 128, 3), (1001, 3)):
         be.dynamic_threshold(a, 0.995, 1.0)
 os.environ.pop("DPM_QUANTILE_IMPL", None)
 be.error_norm(mk(4 * 3 * 1024).reshape(4, -1), mk(4 * 3 * 1024).reshape(4, -1), mk(4 * 3 * 1024).reshape(4, -1), 0.0078, 0.05)
+# round 2: duplicate (TMA copy, two stores), reference-rounding vector kernels, in-kernel Philox noise, the
+# device-side adaptive controller with launches that read their scalars from device memory
+for dt in (torch.float32, torch.bfloat16):
+    be.duplicate(mk(3 * 4 * 33 * 17, dt).reshape(3, 4, 33, 17))
+    be.duplicate(mk(64 * 4 * 64 * 64, dt).reshape(64, 4, 64, 64))
+nr = 8 * 5000 + 5
+be.step(StepArgs(form=5, n_model=2, x=mk(nr), e_cond=mk(nr, torch.bfloat16), e_uncond=mk(nr, torch.bfloat16), m1=mk(nr), m2=mk(nr),
+                 guidance=3.7, want_m_out=True, state_dtype=torch.float32, raw_round=1 | 4, **co))
+be.add_noise_philox(mk(2 * 4 * 17 * 9).reshape(2, 4, 17, 9), [0.9, 0.5, 0.1], [0.43, 0.86, 0.99], torch.float32)
+be.diffedit_corrector(mk(2 * 4 * 16 * 16).reshape(2, 4, 16, 16), mk(2 * 4 * 16 * 16).reshape(2, 4, 16, 16),
+                      (mk(16 * 16).reshape(16, 16) > 0).float(), 0.8, 0.6)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from cases import exact_net, make_betas  # noqa: E402
+from dpm_solver_b200 import DPM_Solver, NoiseScheduleVP, model_wrapper  # noqa: E402
+import contextlib, io  # noqa: E402
+for sched, algo in ((NoiseScheduleVP("linear"), "dpmsolver"), (NoiseScheduleVP("discrete", betas=torch.from_numpy(make_betas("sd")[1])), "dpmsolver++")):
+    s = DPM_Solver(model_wrapper(exact_net, sched), sched, algorithm_type=algo)
+    with contextlib.redirect_stdout(io.StringIO()):
+        s.sample(mk(2 * 3 * 8 * 8).reshape(2, 3, 8, 8), method="adaptive", order=3, t_end=1e-3, solver_type="taylor")
 torch.cuda.synchronize()
 print("sanitize_probe: all kernel families launched")
