@@ -141,13 +141,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   const uint32_t tid = threadIdx.x;
   const uint32_t nthr = blockDim.x;
   const uint32_t tile_pk = nthr * kUnits;
-  // Work split: every CTA owns ONE contiguous range of packets, all ranges equal to within a packet, walked in tiles
-  // of tile_pk packets with a partial last tile. (A round-robin of whole tiles leaves some CTAs one tile short:
-  // 4096 tiles over 148 CTAs is 27.7 each -- 3.6 % of the launch spent waiting for the CTAs that got 28.)
-  const uint32_t per = p.npk / gridDim.x, rem = p.npk % gridDim.x;
-  const uint32_t pk_begin = blockIdx.x * per + min(blockIdx.x, rem);
-  const uint32_t pk_end = pk_begin + per + (blockIdx.x < rem ? 1u : 0u);
-  const uint32_t ntiles = (pk_end - pk_begin + tile_pk - 1) / tile_pk;      // tiles of THIS CTA
+  const uint32_t ntiles = (p.npk + tile_pk - 1) / tile_pk;
   const bool has_x = Needs::kX || (NE > 0 && p.use_xe);  // state slot: x, or xe when no update
   const bool sep_xe = (NE > 0) && p.use_xe && Needs::kX && !p.xe_is_x;  // extra slot: evaluation state
   const bool has_mo = (NE > 0) && (p.m_out != nullptr);
@@ -164,8 +158,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   pdl_wait();   // everything above overlapped the previous launch's tail; global memory from here on
 
   auto issue_loads = [&](uint32_t tile, uint32_t s) {
-    const uint32_t pk0 = pk_begin + tile * tile_pk;
-    const uint32_t pk = min(pk_end - pk0, tile_pk);
+    const uint32_t pk0 = tile * tile_pk;
+    const uint32_t pk = min(p.npk - pk0, tile_pk);
     const uint32_t bs = pk * kBS, bm = pk * kBM;
     const uint64_t os = (uint64_t)pk0 * kBS, om = (uint64_t)pk0 * kBM;
     const uint32_t st = sring + s * L.bytes, bar = sbar + s * 8;
@@ -188,15 +182,17 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
   };
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s)
-      if ((uint32_t)s < ntiles) issue_loads((uint32_t)s, (uint32_t)s);
+    for (int s = 0; s < stages; ++s) {
+      const uint32_t tile = blockIdx.x + (uint32_t)s * gridDim.x;
+      if (tile < ntiles) issue_loads(tile, (uint32_t)s);
+    }
   }
 
   uint32_t slot = 0, parity = 0;
-  for (uint32_t tile = 0; tile < ntiles; ++tile) {
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t st = sring + slot * L.bytes;
-    const uint32_t pk0 = pk_begin + tile * tile_pk;
-    const uint32_t pk_here = min(pk_end - pk0, tile_pk);
+    const uint32_t pk0 = tile * tile_pk;
+    const uint32_t pk_here = min(p.npk - pk0, tile_pk);
 
     mbar_wait32(sbar + slot * 8, parity);
 
@@ -261,8 +257,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads)
         if (has_o2) bulk_s2g32(static_cast<char*>(p.out2) + os, st + L.o, bs);
       }
       bulk_commit();
-      const uint32_t next = tile + (uint32_t)stages;
-      if (next < ntiles) issue_loads(next, slot);
+      const uint32_t next = tile + (uint32_t)stages * gridDim.x;     // < 2^32: ntiles * (1 + stages) never gets near it
+      if (next < ntiles && next > tile) issue_loads(next, slot);
     }
     if (++slot == (uint32_t)stages) { slot = 0; parity ^= 1u; }
   }
