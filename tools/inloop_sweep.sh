@@ -17,7 +17,7 @@ import json, sys
 w, t, c, line = sys.argv[1:5]
 try:
     d = json.loads(line)
-    ks = {k.split("|")[0] + "/" + k.split("|")[1][-1] + k.split("|")[2][-1]: round(v["gbs"]) for k, v in d["kernels"].items()}
+    ks = {(k.split("|")[0] + "/" + k.split("|")[1][-1] + k.split("|")[2][-1]) if k.count("|") == 2 else k: round(v["gbs"]) for k, v in d["kernels"].items()}
     print(f"{w} threads={t} ctas={c}  {d['value']:.1f} GElem/s  {d['ms_per_step']:.3f} ms  {ks}")
 except Exception as e:
     print(f"{w} threads={t} ctas={c}  FAILED {e}: {line[:120]}")
