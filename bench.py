@@ -399,7 +399,7 @@ def make_timed_backend():
             class TimedPrepared:
                 d = prep.d
 
-                def launch(self, tensors):
+                def launch(self, tensors):   # tensors: tuple in PreparedStep.ORDER
                     if not outer.recording:
                         return prep.launch(tensors)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -407,6 +407,7 @@ class PreparedStep:
     __slots__ = ("be", "d", "ref_d", "fn", "n", "dev", "dev_index", "sdt", "mdt", "shape", "shape2", "need_out",
                  "need_m", "fields", "dup", "ptrs", "esize")
 
+    ORDER = ("x", "xe", "m0", "m1", "m2", "e_cond", "e_uncond")     # launch() takes its tensors in this order
     # index of every pointer field inside struct dpm_step_desc (its first 11 members are pointers)
     _PTR = {"x": 0, "xe": 1, "m0": 2, "m1": 3, "m2": 4, "m_out": 5, "out": 6, "out2": 7, "e_cond": 8, "e_uncond": 9}
 
@@ -438,17 +439,18 @@ class PreparedStep:
         self.need_m = a.n_model > 0 and (a.want_m_out or a.form == FORM_NONE)
         self.dup = a.out2 is not None
         # (descriptor field, StepArgs attribute, expected dtype) of every input tensor this launch reads
-        self.fields = tuple((self._PTR[name], name, self.mdt if name in ("e_cond", "e_uncond") else sdt)
-                            for name in ("x", "xe", "m0", "m1", "m2", "e_cond", "e_uncond") if getattr(a, name) is not None)
+        # (pointer slot, position in launch()'s tensor tuple, expected dtype) of every input this launch reads
+        self.fields = tuple((self._PTR[name], pos, self.mdt if name in ("e_cond", "e_uncond") else sdt)
+                            for pos, name in enumerate(self.ORDER) if getattr(a, name) is not None)
         return self
 
-    def launch(self, tensors: dict):
-        """tensors: StepArgs attribute name -> tensor for every input of the frozen launch. Returns
-        (m_out, out, x_in) -- x_in is the doubled CFG batch when the step was prepared with a second output copy --
-        or None when a tensor does not look like the ones the step was prepared for."""
+    def launch(self, tensors: tuple):
+        """tensors: (x, xe, m0, m1, m2, e_cond, e_uncond) (`ORDER`; entries the frozen launch does not read are
+        ignored). Returns (m_out, out, x_in) -- x_in is the doubled CFG batch when the step was prepared with a second
+        output copy -- or None when a tensor does not look like the ones the step was prepared for."""
         n, dev, idx, ptrs = self.n, self.dev, self.dev_index, self.ptrs
-        for f, name, dt in self.fields:
-            t = tensors.get(name)
+        for f, pos, dt in self.fields:
+            t = tensors[pos]
             if t is None or t.dtype is not dt or t.numel() != n or not t.is_contiguous() or t.get_device() != idx:
                 return None
             ptrs[f] = t.data_ptr()

@@ -335,7 +335,8 @@ class DPM_Solver:
         if isinstance(w, WrappedModel) and w.fusable:
             pair = self.__dict__.get("_xin_pair")
             x_in = pair[1] if (pair is not None and pair[0] is x) else None
-            return w.raw(x, t_dev.expand((x.shape[0])), t_input, x_in)
+            # (the continuous label is only read when no precomputed model-input time row is handed over)
+            return w.raw(x, t_dev.expand((x.shape[0])) if t_input is None else None, t_input, x_in)
         return RawOutput(self.model(x, t_dev), None, PARAM_NOISE, 1.0)
 
     def _dup_target(self, x):
@@ -491,12 +492,11 @@ class DPM_Solver:
         be = ops.backend()
         pkey = None
         if slot is not None and self._prep_on:
-            pkey = (slot, raw.param, raw.guidance, raw.e_uncond is None, raw.e_cond.dtype, xe.dtype, tuple(xe.shape),
+            pkey = (slot, raw.param, raw.guidance, raw.e_uncond is None, raw.e_cond.dtype, xe.dtype, xe.shape,
                     want_m, dup_out)
             prep = self._prep_cache.get(pkey)
             if prep is not None:
-                r = prep.launch({"x": x, "xe": xe, "m0": raw.e_cond, "m1": m1, "m2": m2, "e_cond": raw.e_cond,
-                                 "e_uncond": raw.e_uncond})
+                r = prep.launch((x, xe, raw.e_cond, m1, m2, raw.e_cond, raw.e_uncond))
                 if r is not None:
                     m_new, x_next, x_in = r
                     if x_in is not None:
