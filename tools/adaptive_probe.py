@@ -8,8 +8,6 @@ For random adaptive configurations (tests/test_adaptive.py::_adaptive_cfgs) run 
   dev-ctl   : dpm_solver_b200, controller on the device (csrc/adaptive_ctl.cu)
 and print NFE and max|y - y_ref-cpu| / max|y_ref-cpu| for each.
 """
-import contextlib
-import io
 import os
 import sys
 from unittest import mock
