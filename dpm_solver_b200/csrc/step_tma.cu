@@ -19,7 +19,10 @@
 
 namespace dpm {
 
-constexpr int kTmaUnits = 2;   // default packets per thread per tile (tile = threads * units packets)
+#ifndef DPM_TMA_UNITS
+#define DPM_TMA_UNITS 2
+#endif
+constexpr int kTmaUnits = DPM_TMA_UNITS;   // packets per thread per tile (tile = threads * units packets); compile time
 constexpr int kTmaMaxThreads = 512;
 constexpr int kMaxStages = 8;
 
